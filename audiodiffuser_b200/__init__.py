@@ -1,0 +1,17 @@
+"""B200-native EDM sampling / denoising hot path with the reference's Hydra-facing class API.
+
+Drop-in `_target_`s (reference path -> this package):
+    src.models.components.diffusion.EluDiffusion          -> audiodiffuser_b200.components.diffusion.EluDiffusion
+    src.models.components.sampler_edm.EDMSampler          -> audiodiffuser_b200.components.sampler_edm.EDMSampler
+    src.models.components.sampler_edm.EDMAlphaSampler     -> audiodiffuser_b200.components.sampler_edm.EDMAlphaSampler
+    src.models.components.scheduler.KarrasSchedule        -> audiodiffuser_b200.components.scheduler.KarrasSchedule
+    src.models.components.distribution.LogNormalDistribution -> audiodiffuser_b200.components.distribution.LogNormalDistribution
+    src.models.backbones.wavenet.WaveNetNoise             -> audiodiffuser_b200.backbones.wavenet.WaveNetNoise
+"""
+from .components.diffusion import EluDiffusion, Diffusion              # noqa: F401
+from .components.sampler_edm import EDMSampler, EDMAlphaSampler        # noqa: F401
+from .components.scheduler import KarrasSchedule                        # noqa: F401
+from .components.distribution import LogNormalDistribution              # noqa: F401
+from .backbones.wavenet import WaveNetNoise, EDMDenoiser                # noqa: F401
+
+__version__ = "0.1.0"

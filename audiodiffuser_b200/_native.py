@@ -1,0 +1,115 @@
+"""ctypes binding of the C-ABI library `libadb200.so` (include/adb200.h).
+
+There is no CPU or PyTorch fallback: if the library has not been built, or the device is not a
+B200 (sm_100), every call raises. PyTorch only provides device memory (`tensor.data_ptr()`) and the
+current CUDA stream.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, POINTER
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadb200.so")
+
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16}
+TIMER_NAMES = ("conv", "step", "aux")
+
+_lib = None
+
+_F = POINTER(c_float)
+_SIGS = {
+    "adb_last_error": (c_char_p, []),
+    "adb_version": (c_int, []),
+    "adb_device_check": (c_int, [c_int]),
+    "adb_check_async": (c_int, []),
+    "adb_edm_precond_in": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "adb_edm_precond_out": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_float, c_void_p, c_int,
+                                    c_int64, c_void_p]),
+    "adb_edm_scale": (c_int, [c_void_p, c_float, c_void_p, c_int64, c_void_p]),
+    "adb_edm_axpy": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
+    "adb_edm_euler": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
+    "adb_edm_rk2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p,
+                            c_int64, c_void_p]),
+    "adb_edm_noise_in": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                 c_void_p]),
+    "adb_edm_dsm_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int64, c_void_p]),
+    "adb_wavenet_param_count": (c_int64, [c_int, c_int]),
+    "adb_wavenet_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int64, c_int]),
+    "adb_wavenet_destroy": (None, [c_void_p]),
+    "adb_wavenet_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int]),
+    "adb_wavenet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                    c_void_p, c_int64, c_void_p]),
+    "adb_wavenet_forward_debug": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "adb_wavenet_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int,
+                                    c_void_p, c_int64, c_void_p]),
+    "adb_wavenet_sample_edm": (c_int, [c_void_p, c_void_p, _F, c_int, c_int, c_float, c_float, c_float, c_float,
+                                       c_float, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                       c_int64, POINTER(c_int), c_void_p]),
+    "adb_wavenet_set_timing": (c_int, [c_void_p, c_int]),
+    "adb_wavenet_timers": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
+}
+
+
+class AdbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libadb200.so (once). Raises loudly if it is missing — there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AdbError(
+                f"{LIB_PATH} not found: build the sm_100a CUDA library first "
+                "(python -c 'import __graft_entry__ as g; g.build()' or python -m audiodiffuser_b200.build)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise AdbError(f"adb200 error {rc}: {lib().adb_last_error().decode()}")
+
+
+def check_async():
+    """Synchronise and surface asynchronous kernel / pipeline errors."""
+    check(lib().adb_check_async())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise AdbError(f"{name} is on {t.device}: adb200 has no CPU path; move it to a B200")
+    if t.dtype != torch.float32:
+        raise AdbError(f"{name} must be float32 (state and preconditioning are fp32, SURVEY.md §8(b)); got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+_device_ok = set()
+
+
+def ensure_device(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _device_ok:
+        check(lib().adb_device_check(idx))
+        _device_ok.add(idx)
+    return idx

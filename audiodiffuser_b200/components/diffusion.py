@@ -1,0 +1,146 @@
+"""EDM-preconditioned denoiser and DSM loss behind the reference's class API.
+
+Mirrors `src/models/components/diffusion.py`: `Diffusion` base (:15-97) and `EluDiffusion`
+(:220-258). Arithmetic runs in the fused sm_100a kernels of libadb200 (adb_edm_*); when `net` is the
+fused `audiodiffuser_b200.backbones.wavenet.WaveNetNoise` the preconditioning, backbone and eq. 7
+combine run as one device-side sequence (adb_wavenet_denoise). Any other `net` (e.g. a reference
+backbone) is still accepted: only the arithmetic around the call is fused.
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import _native as N
+from .utils import dynamic_threshold_clip, extend_dim, to_batch
+
+
+class Diffusion(nn.Module):
+    """Base class with the reference's `denoise_fn` / `forward` contract (diffusion.py:15-97)."""
+
+    def __init__(self, dynamic_threshold: float = 0.0):
+        super().__init__()
+        self.dynamic_threshold = dynamic_threshold
+
+    def loss_weight(self, sigmas: Tensor) -> Tensor:
+        raise NotImplementedError
+
+    def get_scale_weights(self, sigmas: Tensor, ex_dim: int):
+        raise NotImplementedError
+
+
+class EluDiffusion(Diffusion):
+    """Elucidated diffusion (EDM) preconditioning — diffusion.py:220-258.
+
+    Same constructor: `EluDiffusion(sigma_data, dynamic_threshold=0.0)`.
+    """
+
+    def __init__(self, sigma_data: float, dynamic_threshold: float = 0.0):
+        super().__init__(dynamic_threshold)
+        self.sigma_data = sigma_data
+
+    # -- API parity helpers (tiny [B] tensors; not on the hot path) --------------------------------
+    def get_scale_weights(self, sigmas: Tensor, ex_dim: int) -> Tuple[Tensor, ...]:
+        """(c_skip, c_out, c_in)[B,1..], c_noise[B] — diffusion.py:232-241."""
+        sd = self.sigma_data
+        c_noise = torch.log(sigmas) * 0.25
+        s = extend_dim(sigmas, dim=ex_dim)
+        c_skip = (sd ** 2) / (s ** 2 + sd ** 2)
+        c_out = s * sd * (sd ** 2 + s ** 2) ** -0.5
+        c_in = (s ** 2 + sd ** 2) ** -0.5
+        return c_skip, c_out, c_in, c_noise
+
+    def loss_weight(self, sigmas: Tensor) -> Tensor:
+        """diffusion.py:243-245."""
+        return (sigmas ** 2 + self.sigma_data ** 2) * (sigmas * self.sigma_data) ** -2
+
+    # -- the hot path ------------------------------------------------------------------------------
+    def denoise_fn(self, x_noisy: Tensor, net: nn.Module = None, inference: bool = False, cond_scale: float = 1.0,
+                   sigmas: Optional[Tensor] = None, sigma: Optional[float] = None, **kwargs) -> Tensor:
+        """x0_hat = clip(c_skip x + c_out net(c_in x, c_noise)) — diffusion.py:32-63.
+
+        Exactly one of `sigma` (python float or 0-dim tensor, what every sampler passes) and
+        `sigmas` ([B], training) — utils.py:47.
+        """
+        x = N.require_cuda_f32(x_noisy, "x_noisy")
+        N.ensure_device(x.device)
+        B = x.shape[0]
+        n_per = x[0].numel()
+        sig, stride = to_batch(B, x.device, x=sigma, xs=sigmas)
+        lib = N.lib()
+        st = N.stream_ptr(x.device)
+
+        fused = getattr(net, "_adb_fused_denoise", None)
+        if fused is not None and self.dynamic_threshold == 0.0 and not torch.is_grad_enabled():
+            # unconditional fused backbone: the CFG branch (diffusion.py:52-54) evaluates the same
+            # function twice and lerps identical values, so one evaluation is exact.
+            return fused(x, sig, stride, float(self.sigma_data))
+
+        net_in = torch.empty_like(x)
+        c_noise = torch.empty(B, dtype=torch.float32, device=x.device)
+        N.check(lib.adb_edm_precond_in(N.ptr(x), N.ptr(sig), stride, float(self.sigma_data), N.ptr(net_in),
+                                       N.ptr(c_noise), B, n_per, st))
+        f_null = None
+        if inference:
+            pred = net(net_in, c_noise, cond_drop_prob=0., **kwargs)
+            if cond_scale != 1.0:
+                f_null = net(net_in, c_noise, cond_drop_prob=1., **kwargs)
+        else:
+            pred = net(net_in, c_noise, **kwargs)
+        if pred.shape != x.shape:
+            raise N.AdbError(f"net returned {tuple(pred.shape)}, expected {tuple(x.shape)} "
+                             "(the reference would silently broadcast here, SURVEY.md §0)")
+        if torch.is_grad_enabled() and pred.requires_grad:
+            raise NotImplementedError(
+                "denoise_fn under autograd with a non-fused net: use EluDiffusion.forward (the fused DSM loss) "
+                "or wrap the call in torch.no_grad()")
+        pred = N.require_cuda_f32(pred, "net output")
+        if self.dynamic_threshold != 0.0:
+            c_skip, c_out, _, _ = self.get_scale_weights(sig.expand(B) if stride == 0 else sig, x.ndim)
+            if f_null is not None:
+                pred = f_null + (pred - f_null) * cond_scale
+            return dynamic_threshold_clip(c_skip * x + c_out * pred, self.dynamic_threshold)
+        out = torch.empty_like(x)
+        fn_ptr = N.ptr(N.require_cuda_f32(f_null, "null-cond net output")) if f_null is not None else N.ptr(None)
+        N.check(lib.adb_edm_precond_out(N.ptr(x), N.ptr(pred), fn_ptr, float(cond_scale), N.ptr(sig), stride,
+                                        float(self.sigma_data), N.ptr(out), B, n_per, st))
+        return out
+
+    def forward(self, x: Tensor, net: nn.Module, sigmas: Tensor, inference: bool = False, cond_scale: float = 1.0,
+                noise: Optional[Tensor] = None, **kwargs) -> Tensor:
+        """Denoising-score-matching loss per sample, shape [B] — diffusion.py:65-97.
+
+        `noise` (optional, same shape as x) replaces the internal `torch.randn_like(x)`
+        (diffusion.py:76) so tests can fix it; by default it is drawn exactly like the reference.
+        Forward value only (evaluation / validation loss); see DESIGN.md for the training-step status.
+        """
+        x = N.require_cuda_f32(x, "x")
+        N.ensure_device(x.device)
+        if "x_mask" in kwargs:
+            raise NotImplementedError("x_mask loss masking (diffusion.py:80-81) is outside the fused path")
+        if self.dynamic_threshold != 0.0:
+            raise NotImplementedError("dynamic_threshold != 0 is not supported in the fused loss")
+        B, n_per = x.shape[0], x[0].numel()
+        if noise is None:
+            noise = torch.randn_like(x)
+        noise = N.require_cuda_f32(noise, "noise")
+        sig, _ = to_batch(B, x.device, xs=sigmas)
+        lib, st = N.lib(), N.stream_ptr(x.device)
+        x_noisy = torch.empty_like(x)
+        net_in = torch.empty_like(x)
+        c_noise = torch.empty(B, dtype=torch.float32, device=x.device)
+        N.check(lib.adb_edm_noise_in(N.ptr(x), N.ptr(noise), N.ptr(sig), float(self.sigma_data), N.ptr(x_noisy),
+                                     N.ptr(net_in), N.ptr(c_noise), B, n_per, st))
+        with torch.no_grad():
+            if inference:
+                pred = net(net_in, c_noise, cond_drop_prob=0., **kwargs)
+            else:
+                pred = net(net_in, c_noise, **kwargs)
+        pred = N.require_cuda_f32(pred, "net output")
+        if pred.shape != x.shape:
+            raise N.AdbError(f"net returned {tuple(pred.shape)}, expected {tuple(x.shape)}")
+        loss = torch.empty(B, dtype=torch.float32, device=x.device)
+        N.check(lib.adb_edm_dsm_loss(N.ptr(x), N.ptr(x_noisy), N.ptr(pred), N.ptr(sig), float(self.sigma_data),
+                                     N.ptr(loss), B, n_per, st))
+        return loss

@@ -1,0 +1,199 @@
+"""EDM samplers behind the reference's class API.
+
+Mirrors `src/models/components/sampler_edm.py`: `EDMSampler` (:302-397, Heun/Euler + churn) and
+`EDMAlphaSampler` (:229-300, general 2nd-order Runge-Kutta). Same constructors and
+`forward(noise, fn, net, sigmas, **kwargs)` / `step(...)` signatures.
+
+Two execution modes, chosen per call:
+  * fused trajectory — `fn` is `EluDiffusion.denoise_fn` of this package and `net` is the fused
+    DiffWave backbone: the whole N-step loop (preconditioning, 2N-1 network evaluations, Heun
+    updates, churn) runs device-side through one C call (adb_wavenet_sample_edm), with per-step
+    scalars computed once on the host — no per-step host synchronisation.
+  * generic — any other `fn` / `net` (e.g. a reference backbone): the loop stays in Python, the
+    update arithmetic runs in the fused elementwise kernels (adb_edm_euler / adb_edm_rk2 / ...).
+"""
+from math import sqrt
+from typing import Callable, List, Optional
+
+import ctypes
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import _native as N
+
+
+def _host_sigmas(sigmas: Tensor) -> List[float]:
+    """One device->host copy per trajectory (the reference syncs 2-4 times per step)."""
+    return [float(v) for v in sigmas.detach().to(torch.float32).cpu().tolist()]
+
+
+def _f32(v: float) -> float:
+    """Round a python double to fp32 (the reference's scalars live in fp32 tensors)."""
+    return ctypes.c_float(v).value
+
+
+def _fused_target(fn, net):
+    diff = getattr(fn, "__self__", None)
+    if diff is None or getattr(fn, "__name__", "") != "denoise_fn":
+        return None
+    if not hasattr(diff, "sigma_data") or getattr(diff, "dynamic_threshold", 0.0) != 0.0:
+        return None
+    if getattr(net, "_adb_fused_sample", None) is None:
+        return None
+    return diff
+
+
+class EDMSampler(nn.Module):
+    """EDM stochastic sampler (Heun + churn) — sampler_edm.py:302-397."""
+
+    def __init__(self, s_tmin: float = 0, s_tmax: float = float('inf'), s_churn: float = 150.0, s_noise: float = 1.04,
+                 num_steps: int = 200, cond_scale: float = 1.0, use_heun: bool = True):
+        super().__init__()
+        self.s_tmin = s_tmin
+        self.s_tmax = s_tmax
+        self.s_noise = s_noise
+        self.s_churn = s_churn
+        self.num_steps = num_steps
+        self.cond_scale = cond_scale
+        self.use_heun = use_heun
+        self.last_nfe = 0
+
+    def _gamma(self, sigma: float) -> float:
+        on = _f32(min(self.s_churn / self.num_steps, sqrt(2) - 1))       # sampler_edm.py:383-387
+        return on if (self.s_tmin <= sigma <= self.s_tmax) else 0.0
+
+    def step(self, x: Tensor, fn: Callable, net: nn.Module, sigma: float, sigma_next: float, gamma: float,
+             eps: Optional[Tensor] = None, **kwargs) -> Tensor:
+        """One step (sampler_edm.py:333-369). sigma / sigma_next / gamma: python floats or 0-dim tensors."""
+        sigma, sigma_next, gamma = (_f32(float(v)) for v in (sigma, sigma_next, gamma))
+        x = N.require_cuda_f32(x, "x")
+        lib, st, n = N.lib(), N.stream_ptr(x.device), x.numel()
+        if eps is None:
+            eps = torch.randn_like(x)                 # drawn every step, like sampler_edm.py:346
+        if gamma > 0:
+            sigma_hat = _f32(sigma + _f32(gamma * sigma))
+            a = _f32(sqrt(_f32(_f32(sigma_hat * sigma_hat) - _f32(sigma * sigma))))
+            eps = N.require_cuda_f32(eps, "eps")
+            noise = torch.empty_like(x)
+            N.check(lib.adb_edm_scale(N.ptr(eps), float(self.s_noise), N.ptr(noise), n, st))
+            x_hat = torch.empty_like(x)
+            N.check(lib.adb_edm_axpy(N.ptr(x), N.ptr(noise), a, N.ptr(x_hat), n, st))
+        else:
+            sigma_hat, x_hat = sigma, x
+        den = N.require_cuda_f32(fn(x_hat, net=net, sigma=sigma_hat, inference=True, cond_scale=self.cond_scale,
+                                    **kwargs), "denoised")
+        self.last_nfe += 1
+        h = _f32(sigma_next - sigma_hat)
+        d = torch.empty_like(x)
+        x_next = torch.empty_like(x)
+        N.check(lib.adb_edm_euler(N.ptr(x_hat), N.ptr(den), sigma_hat, h, N.ptr(d), N.ptr(x_next), n, st))
+        if sigma_next != 0 and self.use_heun:
+            den2 = N.require_cuda_f32(fn(x_next, net=net, sigma=sigma_next, inference=True,
+                                         cond_scale=self.cond_scale, **kwargs), "denoised")
+            self.last_nfe += 1
+            out = torch.empty_like(x)
+            N.check(lib.adb_edm_rk2(N.ptr(x_hat), N.ptr(d), N.ptr(x_next), N.ptr(den2), sigma_next, h, 0.5, 0.5,
+                                    N.ptr(out), n, st))
+            x_next = out
+        return x_next
+
+    @torch.no_grad()
+    def forward(self, noise: Tensor, fn: Callable, net: nn.Module, sigmas: Tensor, eps: Optional[Tensor] = None,
+                **kwargs) -> Tensor:
+        """noise [B,C,L] ~ N(0,1), sigmas [N] -> x [B,C,L] (sampler_edm.py:371-397).
+
+        `eps` (optional, [num_steps, *noise.shape]) fixes the churn noise for parity tests; by
+        default one `randn_like(x)` is drawn per step in the reference's order.
+        """
+        noise = N.require_cuda_f32(noise, "noise")
+        N.ensure_device(noise.device)
+        sig = _host_sigmas(sigmas)
+        if len(sig) < self.num_steps:
+            raise ValueError(f"schedule has {len(sig)} sigmas but num_steps={self.num_steps} (sampler_edm.py:390)")
+        self.last_nfe = 0
+        churn = any(self._gamma(s) > 0 for s in sig[:self.num_steps])
+        if eps is None and churn:
+            eps = torch.empty((self.num_steps,) + tuple(noise.shape), dtype=torch.float32, device=noise.device)
+            for i in range(self.num_steps):
+                eps[i].normal_()                      # same RNG consumption as randn_like per step
+        diff = _fused_target(fn, net)
+        if diff is not None and not kwargs.get("_force_generic", False):
+            x, nfe = net._adb_fused_sample(noise, sig, self.num_steps, float(diff.sigma_data), float(self.s_tmin),
+                                           float(min(self.s_tmax, 3.0e38)), float(self.s_churn), float(self.s_noise),
+                                           bool(self.use_heun), -1.0, eps if churn else None)
+            self.last_nfe = nfe
+            return x
+        kwargs.pop("_force_generic", None)
+        sig = sig + [0.0]                              # t_N = 0 (sampler_edm.py:377)
+        x = torch.empty_like(noise)
+        N.check(N.lib().adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), x.numel(), N.stream_ptr(x.device)))
+        for i in range(self.num_steps):
+            e = eps[i] if eps is not None else None
+            if e is None and not churn:
+                e = x                                  # unused when gamma == 0; skip the RNG call
+            x = self.step(x, fn=fn, net=net, sigma=sig[i], sigma_next=sig[i + 1], gamma=self._gamma(sig[i]),
+                          eps=e, **kwargs)
+        return x
+
+
+class EDMAlphaSampler(nn.Module):
+    """EDM deterministic sampler with a general 2nd-order Runge-Kutta step (alpha = 1: Heun) —
+    sampler_edm.py:229-300."""
+
+    def __init__(self, alpha: float = 1.0, num_steps: int = 50, cond_scale: float = 1.0, use_heun: bool = True):
+        super().__init__()
+        self.alpha = alpha
+        self.num_steps = num_steps
+        self.cond_scale = cond_scale
+        self.use_heun = use_heun
+        self.last_nfe = 0
+
+    @torch.no_grad()
+    def step(self, x: Tensor, fn: Callable, net: nn.Module, sigma: float, sigma_next: float, **kwargs) -> Tensor:
+        """sampler_edm.py:251-282."""
+        sigma, sigma_next = _f32(float(sigma)), _f32(float(sigma_next))
+        x = N.require_cuda_f32(x, "x")
+        lib, st, n = N.lib(), N.stream_ptr(x.device), x.numel()
+        h = _f32(sigma_next - sigma)
+        den = N.require_cuda_f32(fn(x, net=net, sigma=sigma, inference=True, cond_scale=self.cond_scale, **kwargs),
+                                 "denoised")
+        self.last_nfe += 1
+        ah = _f32(self.alpha * h)
+        sigma_p = _f32(sigma + ah)
+        d = torch.empty_like(x)
+        x_p = torch.empty_like(x)
+        if sigma_p != 0 and self.use_heun:
+            N.check(lib.adb_edm_euler(N.ptr(x), N.ptr(den), sigma, ah, N.ptr(d), N.ptr(x_p), n, st))
+            den_p = N.require_cuda_f32(fn(x_p, net=net, sigma=sigma_p, inference=True, cond_scale=self.cond_scale,
+                                          **kwargs), "denoised")
+            self.last_nfe += 1
+            out = torch.empty_like(x)
+            w1 = 0.5 / self.alpha
+            N.check(lib.adb_edm_rk2(N.ptr(x), N.ptr(d), N.ptr(x_p), N.ptr(den_p), sigma_p, h, _f32(1 - w1), _f32(w1),
+                                    N.ptr(out), n, st))
+            return out
+        N.check(lib.adb_edm_euler(N.ptr(x), N.ptr(den), sigma, h, N.ptr(d), N.ptr(x_p), n, st))
+        return x_p
+
+    @torch.no_grad()
+    def forward(self, noise: Tensor, fn: Callable, net: nn.Module, sigmas: Tensor, **kwargs) -> Tensor:
+        """sampler_edm.py:284-300 — loops num_steps - 1 times and never appends sigma = 0."""
+        noise = N.require_cuda_f32(noise, "noise")
+        N.ensure_device(noise.device)
+        sig = _host_sigmas(sigmas)
+        if len(sig) < self.num_steps:
+            raise ValueError(f"schedule has {len(sig)} sigmas but num_steps={self.num_steps}")
+        self.last_nfe = 0
+        diff = _fused_target(fn, net)
+        if diff is not None and not kwargs.get("_force_generic", False):
+            x, nfe = net._adb_fused_sample(noise, sig, self.num_steps, float(diff.sigma_data), 0.0, 3.0e38, 0.0, 1.0,
+                                           bool(self.use_heun), float(self.alpha), None)
+            self.last_nfe = nfe
+            return x
+        kwargs.pop("_force_generic", None)
+        x = torch.empty_like(noise)
+        N.check(N.lib().adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), x.numel(), N.stream_ptr(x.device)))
+        for i in range(self.num_steps - 1):
+            x = self.step(x, fn=fn, net=net, sigma=sig[i], sigma_next=sig[i + 1], **kwargs)
+        return x

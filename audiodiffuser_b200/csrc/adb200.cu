@@ -1,0 +1,849 @@
+// adb200 — C-ABI entry points (include/adb200.h) over the sm_100a kernels in this directory.
+// Single translation unit: the kernel headers are included here so that device globals (the
+// spin-guard word) exist exactly once.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/adb200.h"
+#include "ptx.cuh"
+#include "edm_kernels.cuh"
+#include "wavenet_f32.cuh"
+#include "wavenet_tc.cuh"
+
+using namespace adb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ADB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define REQUIRE(cond, ...)                                 \
+    do {                                                   \
+        if (!(cond)) return fail(ADB_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+extern "C" const char* adb_last_error(void) { return g_err.c_str(); }
+extern "C" int adb_version(void) { return 100; }
+
+extern "C" int adb_device_check(int device) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ADB_ERR_UNSUPPORTED, "device %d is sm_%d%d; adb200 contains sm_100a code only", device, prop.major,
+                    prop.minor);
+    return ADB_OK;
+}
+
+extern "C" int adb_check_async(void) {
+    CK(cudaDeviceSynchronize());
+    SpinGuardState st;
+    CK(cudaMemcpyFromSymbol(&st, g_spin_guard, sizeof st));
+    if (st.abort_flag) {
+        SpinGuardState zero = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_spin_guard, &zero, sizeof zero);
+        return fail(ADB_ERR_PIPELINE, "in-kernel barrier wait timed out: site=%u block=%u aux=%u", st.site, st.block,
+                    st.aux);
+    }
+    return ADB_OK;
+}
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------------------------------------
+// EDM elementwise entry points
+// ------------------------------------------------------------------------------------------------
+static EdmArgs edm_args(const float* x, const float* in1, const float* in2, float* o0, float* o1, int64_t n_per,
+                        int64_t total) {
+    EdmArgs p;
+    memset(&p, 0, sizeof p);
+    p.x = x; p.in1 = in1; p.in2 = in2; p.out0 = o0; p.out1 = o1;
+    p.n_per = n_per; p.total = total;
+    return p;
+}
+static inline float sd2_of(float sigma_data) {
+    const double d = static_cast<double>(sigma_data);
+    return static_cast<float>(d * d);
+}
+
+extern "C" int adb_edm_precond_in(const float* x, const float* sigmas, int sigma_stride, float sigma_data, float* net_in,
+                                  float* c_noise, int B, int64_t n_per, void* stream) {
+    REQUIRE(x && sigmas && net_in && B > 0 && n_per > 0, "adb_edm_precond_in: bad arguments");
+    REQUIRE(sigma_stride == 0 || sigma_stride == 1, "sigma_stride must be 0 or 1");
+    EdmArgs p = edm_args(x, nullptr, nullptr, net_in, nullptr, n_per, n_per * B);
+    p.sigmas = sigmas; p.sigma_stride = sigma_stride; p.sigma_data = sigma_data; p.sd2 = sd2_of(sigma_data);
+    CK(edm_launch<OP_SCALE_IN>(p, nullptr, S(stream)));
+    if (c_noise) {
+        edm_cnoise_kernel<<<(B + 255) / 256, 256, 0, S(stream)>>>(sigmas, sigma_stride, c_noise, B);
+        CK(cudaGetLastError());
+    }
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_precond_out(const float* x, const float* f, const float* f_null, float cond_scale,
+                                   const float* sigmas, int sigma_stride, float sigma_data, float* out, int B,
+                                   int64_t n_per, void* stream) {
+    REQUIRE(x && f && sigmas && out && B > 0 && n_per > 0, "adb_edm_precond_out: bad arguments");
+    REQUIRE(sigma_stride == 0 || sigma_stride == 1, "sigma_stride must be 0 or 1");
+    EdmArgs p = edm_args(x, f, f_null, out, nullptr, n_per, n_per * B);
+    p.sigmas = sigmas; p.sigma_stride = sigma_stride; p.sigma_data = sigma_data; p.sd2 = sd2_of(sigma_data);
+    p.cond_scale = cond_scale;
+    if (f_null) CK(edm_launch<OP_COMBINE_CFG>(p, nullptr, S(stream)));
+    else        CK(edm_launch<OP_COMBINE>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_scale(const float* x, float a, float* out, int64_t n, void* stream) {
+    REQUIRE(x && out && n > 0, "adb_edm_scale: bad arguments");
+    EdmArgs p = edm_args(x, nullptr, nullptr, out, nullptr, n, n);
+    p.a = a;
+    CK(edm_launch<OP_SCALE>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_axpy(const float* x, const float* e, float a, float* out, int64_t n, void* stream) {
+    REQUIRE(x && e && out && n > 0, "adb_edm_axpy: bad arguments");
+    EdmArgs p = edm_args(x, e, nullptr, out, nullptr, n, n);
+    p.a = a;
+    CK(edm_launch<OP_AXPY>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_euler(const float* x, const float* den, float sigma, float h, float* d, float* x_next, int64_t n,
+                             void* stream) {
+    REQUIRE(x && den && d && x_next && n > 0, "adb_edm_euler: bad arguments");
+    EdmArgs p = edm_args(x, den, nullptr, d, x_next, n, n);
+    p.s0 = sigma; p.h = h;
+    CK(edm_launch<OP_EULER>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_rk2(const float* x, const float* d, const float* x1, const float* den1, float sigma1, float h,
+                           float w0, float w1, float* out, int64_t n, void* stream) {
+    REQUIRE(x && d && x1 && den1 && out && n > 0, "adb_edm_rk2: bad arguments");
+    EdmArgs p = edm_args(x, den1, x1, out, nullptr, n, n);
+    p.s1 = sigma1; p.h = h; p.w0 = w0; p.w1 = w1;
+    if (w0 == 0.5f && w1 == 0.5f) {
+        p.hh = 0.5f * h;                       // 0.5 * (sigma_next - sigma_hat), sampler_edm.py:367
+        CK(edm_launch<OP_HEUN>(p, d, S(stream)));
+    } else {
+        CK(edm_launch<OP_RK2>(p, d, S(stream)));
+    }
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_noise_in(const float* x, const float* noise, const float* sigmas, float sigma_data, float* x_noisy,
+                                float* net_in, float* c_noise, int B, int64_t n_per, void* stream) {
+    REQUIRE(x && noise && sigmas && x_noisy && net_in && B > 0 && n_per > 0, "adb_edm_noise_in: bad arguments");
+    EdmArgs p = edm_args(x, noise, nullptr, x_noisy, net_in, n_per, n_per * B);
+    p.sigmas = sigmas; p.sigma_stride = 1; p.sigma_data = sigma_data; p.sd2 = sd2_of(sigma_data);
+    CK(edm_launch<OP_NOISE_IN>(p, nullptr, S(stream)));
+    if (c_noise) {
+        edm_cnoise_kernel<<<(B + 255) / 256, 256, 0, S(stream)>>>(sigmas, 1, c_noise, B);
+        CK(cudaGetLastError());
+    }
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_dsm_loss(const float* x, const float* x_noisy, const float* f, const float* sigmas,
+                                float sigma_data, float* loss, int B, int64_t n_per, void* stream) {
+    REQUIRE(x && x_noisy && f && sigmas && loss && B > 0 && n_per > 0, "adb_edm_dsm_loss: bad arguments");
+    CK(cudaMemsetAsync(loss, 0, sizeof(float) * B, S(stream)));
+    int chunks = static_cast<int>((n_per + 8191) / 8192);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    edm_dsm_loss_kernel<<<B * chunks, 256, 0, S(stream)>>>(x, x_noisy, f, sigmas, sigma_data, sd2_of(sigma_data), loss,
+                                                           n_per, chunks);
+    CK(cudaGetLastError());
+    return ADB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DiffWave handle
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+struct LayerW {
+    // views into the flat parameter copy
+    const float *v1, *g1, *b1, *wp, *bp, *v2, *g2, *b2;
+    // folded fp32 (owned)
+    float *w1f, *w2f;
+};
+
+struct TimerPair {
+    cudaEvent_t a, b;
+    int cls;
+};
+
+struct HMap {
+    const void* ptr;
+    int B, L;
+    CUtensorMap map;
+};
+
+struct adb_wavenet {
+    int C = 0, layers = 0, cycle = 0;
+    int64_t n_params = 0;
+    float* params = nullptr;          // device copy of the flat vector
+    std::vector<LayerW> L;
+    const float *v_in, *g_in, *b_in, *fc1w, *fc1b, *fc2w, *fc2b, *v_sp, *g_sp, *b_sp, *w_out, *b_out;
+    float* w_in_f = nullptr;          // folded [C]
+    float* wsp_f = nullptr;           // folded [C][C] (ci, co)
+    const float** d_wp = nullptr;     // device arrays of per-layer pointers
+    const float** d_bp = nullptr;
+    // tensor-core path (C == 256 only)
+    __nv_bfloat16* wtc = nullptr;     // [layers][32][256][64]
+    __nv_bfloat16* wsp_tc = nullptr;  // [4][256][64]
+    float* mtab = nullptr;            // [512][layers*3*512]  (W1[tap] Wp)^T
+    float* cvec = nullptr;            // [layers*3*512]       W1[tap] bp (+ b1 for the centre tap)
+    CUtensorMap tm_w, tm_wsp;
+    std::vector<HMap> hmaps;
+    bool tc_ready = false;
+    // timing
+    bool timing = false;
+    std::vector<TimerPair> timers;
+    size_t timers_used = 0;
+    double ms_acc[ADB_TIMER_COUNT] = {0, 0, 0};
+    int64_t launches[ADB_TIMER_COUNT] = {0, 0, 0};
+    std::vector<void*> owned;
+};
+
+struct ScopedTimer {
+    adb_wavenet* n;
+    cudaStream_t s;
+    int idx = -1;
+    ScopedTimer(adb_wavenet* net, int cls, cudaStream_t st) : n(net), s(st) {
+        n->launches[cls]++;
+        if (!n->timing) return;
+        if (n->timers_used == n->timers.size()) {
+            TimerPair t;
+            cudaEventCreate(&t.a);
+            cudaEventCreate(&t.b);
+            n->timers.push_back(t);
+        }
+        idx = static_cast<int>(n->timers_used++);
+        n->timers[idx].cls = cls;
+        cudaEventRecord(n->timers[idx].a, s);
+    }
+    ~ScopedTimer() {
+        if (idx >= 0) cudaEventRecord(n->timers[idx].b, s);
+    }
+};
+
+extern "C" int adb_wavenet_set_timing(adb_wavenet* net, int enabled) {
+    REQUIRE(net, "null handle");
+    net->timing = enabled != 0;
+    net->timers_used = 0;
+    for (int i = 0; i < ADB_TIMER_COUNT; ++i) { net->ms_acc[i] = 0; net->launches[i] = 0; }
+    return ADB_OK;
+}
+
+extern "C" int adb_wavenet_timers(adb_wavenet* net, double* ms_out, int64_t* launches_out) {
+    REQUIRE(net, "null handle");
+    CK(cudaDeviceSynchronize());
+    for (size_t i = 0; i < net->timers_used; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, net->timers[i].a, net->timers[i].b));
+        net->ms_acc[net->timers[i].cls] += ms;
+    }
+    net->timers_used = 0;
+    for (int i = 0; i < ADB_TIMER_COUNT; ++i) {
+        if (ms_out) ms_out[i] = net->ms_acc[i];
+        if (launches_out) launches_out[i] = net->launches[i];
+    }
+    return ADB_OK;
+}
+
+extern "C" int64_t adb_wavenet_param_count(int C, int layers) {
+    int64_t n = 0;
+    n += C + 1 + C;                                   // input_projection: bias, g, v[C][1][1]
+    n += 512 * 128 + 512 + 512 * 512 + 512;           // fc_t1, fc_t2
+    n += static_cast<int64_t>(layers) * (2 * C + 1 + 2LL * C * C * 3 + C * 512LL + C + 2 * C + 1 + 2LL * C * C);
+    n += C + 1 + static_cast<int64_t>(C) * C;         // skip_projection
+    n += C + 1;                                       // output_projection (ZeroConv1d): weight [1][C][1], bias
+    return n;
+}
+
+template <typename T>
+static cudaError_t dmalloc(adb_wavenet* n, T** p, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+    if (e == cudaSuccess) n->owned.push_back(*p);
+    return e;
+}
+
+static int make_weight_map(CUtensorMap* map, const void* base, uint64_t rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 256};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", static_cast<int>(r));
+    return ADB_OK;
+}
+
+// 3-D map over channels-last activations [B][L][256] bf16, box [64 ch][128 t][1]; out-of-range time
+// coordinates (negative or >= L) are zero-filled, which is the convolution's zero padding.
+static int make_h_map(CUtensorMap* map, const void* base, int B, int L) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {256, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {512, static_cast<cuuint64_t>(L) * 512};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled(h) failed: %d", static_cast<int>(r));
+    return ADB_OK;
+}
+
+static int get_h_map(adb_wavenet* n, const void* ptr, int B, int L, const CUtensorMap** out) {
+    for (auto& m : n->hmaps)
+        if (m.ptr == ptr && m.B == B && m.L == L) { *out = &m.map; return ADB_OK; }
+    if (n->hmaps.size() > 64) n->hmaps.clear();
+    HMap m;
+    m.ptr = ptr; m.B = B; m.L = L;
+    int rc = make_h_map(&m.map, ptr, B, L);
+    if (rc) return rc;
+    n->hmaps.push_back(m);
+    *out = &n->hmaps.back().map;
+    return ADB_OK;
+}
+
+extern "C" void adb_wavenet_destroy(adb_wavenet* net) {
+    if (!net) return;
+    for (void* p : net->owned) cudaFree(p);
+    for (auto& t : net->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    delete net;
+}
+
+extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycle, const float* params, int64_t n_params,
+                                  int on_device) {
+    REQUIRE(out && params, "adb_wavenet_create: null argument");
+    REQUIRE(C >= 64 && C % 64 == 0, "residual_channels must be a positive multiple of 64 (got %d)", C);
+    REQUIRE(layers >= 1 && cycle >= 1, "bad layer / cycle count");
+    REQUIRE(n_params == adb_wavenet_param_count(C, layers), "parameter vector has %lld values, expected %lld",
+            static_cast<long long>(n_params), static_cast<long long>(adb_wavenet_param_count(C, layers)));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int rc = adb_device_check(dev);
+    if (rc) return rc;
+
+    adb_wavenet* n = new adb_wavenet();
+    n->C = C; n->layers = layers; n->cycle = cycle; n->n_params = n_params;
+#define CKN(expr)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            adb_wavenet_destroy(n);                                                                 \
+            return fail(ADB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                           \
+    } while (0)
+    CKN(dmalloc(n, &n->params, n_params));
+    CKN(cudaMemcpy(n->params, params, sizeof(float) * n_params, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+
+    // ---- carve the flat vector in state_dict order (wavenet.py:153-168) ----
+    const float* p = n->params;
+    auto take = [&](int64_t cnt) { const float* r = p; p += cnt; return r; };
+    n->b_in = take(C); n->g_in = take(1); n->v_in = take(C);
+    n->fc1w = take(512 * 128); n->fc1b = take(512); n->fc2w = take(512 * 512); n->fc2b = take(512);
+    n->L.resize(layers);
+    for (int l = 0; l < layers; ++l) {
+        LayerW& w = n->L[l];
+        w.b1 = take(2 * C); w.g1 = take(1); w.v1 = take(2LL * C * C * 3);
+        w.wp = take(C * 512LL); w.bp = take(C);
+        w.b2 = take(2 * C); w.g2 = take(1); w.v2 = take(2LL * C * C);
+    }
+    n->b_sp = take(C); n->g_sp = take(1); n->v_sp = take(static_cast<int64_t>(C) * C);
+    n->w_out = take(C); n->b_out = take(1);
+    if (p - n->params != n_params) { adb_wavenet_destroy(n); return fail(ADB_ERR_INVALID, "internal: parameter carve mismatch"); }
+
+    // ---- weight-norm scales: one block per weight-normed conv ----
+    const int njobs = 2 * layers + 2;
+    std::vector<WnJob> jobs(njobs);
+    jobs[0] = {n->v_in, n->g_in, C};
+    for (int l = 0; l < layers; ++l) {
+        jobs[1 + 2 * l] = {n->L[l].v1, n->L[l].g1, 2LL * C * C * 3};
+        jobs[2 + 2 * l] = {n->L[l].v2, n->L[l].g2, 2LL * C * C};
+    }
+    jobs[njobs - 1] = {n->v_sp, n->g_sp, static_cast<long long>(C) * C};
+    WnJob* d_jobs = nullptr;
+    float* d_scale = nullptr;
+    CKN(cudaMalloc(&d_jobs, sizeof(WnJob) * njobs));
+    CKN(cudaMalloc(&d_scale, sizeof(float) * njobs));
+    CKN(cudaMemcpy(d_jobs, jobs.data(), sizeof(WnJob) * njobs, cudaMemcpyHostToDevice));
+    wn_scale_kernel<<<njobs, 256>>>(d_jobs, d_scale);
+    CKN(cudaGetLastError());
+
+    // ---- folded fp32 weights ----
+    CKN(dmalloc(n, &n->w_in_f, C));
+    scale_copy_kernel<<<1, 256>>>(n->v_in, d_scale + 0, n->w_in_f, C);
+    CKN(dmalloc(n, &n->wsp_f, static_cast<size_t>(C) * C));
+    pack_conv_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->v_sp, d_scale + njobs - 1, n->wsp_f, C, C, 1);
+    std::vector<const float*> h_wp(layers), h_bp(layers);
+    for (int l = 0; l < layers; ++l) {
+        LayerW& w = n->L[l];
+        CKN(dmalloc(n, &w.w1f, 3ULL * C * 2 * C));
+        CKN(dmalloc(n, &w.w2f, 2ULL * C * C));
+        pack_conv_f32_kernel<<<grid_for(6LL * C * C), 256>>>(w.v1, d_scale + 1 + 2 * l, w.w1f, 2 * C, C, 3);
+        pack_conv_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.v2, d_scale + 2 + 2 * l, w.w2f, 2 * C, C, 1);
+        h_wp[l] = w.wp; h_bp[l] = w.bp;
+    }
+    CKN(cudaGetLastError());
+    CKN(dmalloc(n, &n->d_wp, layers));
+    CKN(dmalloc(n, &n->d_bp, layers));
+    CKN(cudaMemcpy(n->d_wp, h_wp.data(), sizeof(float*) * layers, cudaMemcpyHostToDevice));
+    CKN(cudaMemcpy(n->d_bp, h_bp.data(), sizeof(float*) * layers, cudaMemcpyHostToDevice));
+
+    // ---- tensor-core packing (C == 256) ----
+    if (C == TC_C) {
+        const size_t wtc_elems = static_cast<size_t>(layers) * 32 * 256 * 64;
+        CKN(dmalloc(n, &n->wtc, wtc_elems));
+        CKN(dmalloc(n, &n->wsp_tc, 4ULL * 256 * 64));
+        const long long ldm = static_cast<long long>(layers) * 1536;
+        CKN(dmalloc(n, &n->mtab, 512ULL * ldm));
+        CKN(dmalloc(n, &n->cvec, static_cast<size_t>(ldm)));
+        float* wpT = nullptr;
+        CKN(cudaMalloc(&wpT, sizeof(float) * 512 * C));
+        for (int l = 0; l < layers; ++l) {
+            LayerW& w = n->L[l];
+            pack_tc_layer_kernel<<<148 * 4, 256>>>(w.w1f, w.w2f, n->wtc + static_cast<size_t>(l) * 32 * 256 * 64);
+            transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, wpT, C, 512);     // [C][512] -> [512][C]
+            for (int tap = 0; tap < 3; ++tap) {
+                ConvF32Args a;
+                memset(&a, 0, sizeof a);
+                // mtab[k][l,tap,co] = sum_ci Wp[ci][k] * W1[tap][ci][co]
+                a.in = wpT; a.w = w.w1f + static_cast<size_t>(tap) * C * 2 * C; a.out = n->mtab + (l * 3 + tap) * 512;
+                a.nb = 1; a.L = 512; a.Cin = C; a.Cout = 2 * C; a.taps = 1; a.dil = 1;
+                a.ldw = 2 * C; a.ldo = ldm; a.in_scale = 1.f;
+                CKN(conv_cl_f32(a, 0));
+                // cvec[l,tap,co] = sum_ci bp[ci] * W1[tap][ci][co] (+ b1[co] for the centre tap)
+                a.in = w.bp; a.out = n->cvec + (l * 3 + tap) * 512; a.L = 1; a.ldo = 2 * C;
+                a.bias = (tap == 1) ? w.b1 : nullptr;
+                CKN(conv_cl_f32(a, 0));
+            }
+            CKN(cudaDeviceSynchronize());      // wpT is reused by the next layer
+        }
+        pack_tc_tail_kernel<<<64, 256>>>(n->wsp_f, n->wsp_tc);
+        CKN(cudaGetLastError());
+        CKN(cudaDeviceSynchronize());
+        cudaFree(wpT);
+        int rc2 = make_weight_map(&n->tm_w, n->wtc, static_cast<uint64_t>(layers) * 32 * 256);
+        if (!rc2) rc2 = make_weight_map(&n->tm_wsp, n->wsp_tc, 4 * 256);
+        if (rc2) { adb_wavenet_destroy(n); cudaFree(d_jobs); cudaFree(d_scale); return rc2; }
+        CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
+        n->tc_ready = true;
+    }
+    CKN(cudaDeviceSynchronize());
+    cudaFree(d_jobs);
+    cudaFree(d_scale);
+#undef CKN
+    *out = n;
+    return ADB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+    // shared
+    float *emb, *c_noise, *c_in;        // [B][512], [B], [B]
+    float *xhat, *dslope, *fbuf, *xnext;  // sampler state, [B][L] each
+    // fp32 path
+    float *proj, *hA, *hB, *y, *z, *o, *skip, *s2;
+    // bf16 path
+    float* E;                            // [B][layers*1536]
+    __nv_bfloat16 *hbA, *hbB;
+    int64_t total;
+};
+
+static Workspace carve(const adb_wavenet* n, int B, int L, int precision, void* base) {
+    Workspace w;
+    memset(&w, 0, sizeof w);
+    uint8_t* p = reinterpret_cast<uint8_t*>(base);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        uint8_t* r = p ? p + off : nullptr;
+        off += (bytes + 1023) / 1024 * 1024;
+        return r;
+    };
+    const int64_t BL = static_cast<int64_t>(B) * L, C = n->C;
+    w.emb = reinterpret_cast<float*>(take(B * 512LL * 4));
+    w.c_noise = reinterpret_cast<float*>(take(B * 4LL));
+    w.c_in = reinterpret_cast<float*>(take(B * 4LL));
+    w.xhat = reinterpret_cast<float*>(take(BL * 4));
+    w.dslope = reinterpret_cast<float*>(take(BL * 4));
+    w.fbuf = reinterpret_cast<float*>(take(BL * 4));
+    w.xnext = reinterpret_cast<float*>(take(BL * 4));
+    w.skip = reinterpret_cast<float*>(take(BL * C * 4));
+    if (precision == ADB_PRECISION_FP32) {
+        w.proj = reinterpret_cast<float*>(take(static_cast<int64_t>(n->layers) * B * C * 4));
+        w.hA = reinterpret_cast<float*>(take(BL * C * 4));
+        w.hB = reinterpret_cast<float*>(take(BL * C * 4));
+        w.y = reinterpret_cast<float*>(take(BL * 2 * C * 4));
+        w.z = reinterpret_cast<float*>(take(BL * C * 4));
+        w.o = reinterpret_cast<float*>(take(BL * 2 * C * 4));
+        w.s2 = reinterpret_cast<float*>(take(BL * C * 4));
+    } else {
+        w.E = reinterpret_cast<float*>(take(static_cast<int64_t>(B) * n->layers * 1536 * 4));
+        w.hbA = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
+        w.hbB = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
+    }
+    w.total = off;
+    return w;
+}
+
+extern "C" int64_t adb_wavenet_workspace_bytes(const adb_wavenet* net, int B, int L, int precision) {
+    if (!net || B <= 0 || L <= 0) return -1;
+    return carve(net, B, L, precision, nullptr).total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void cvt_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = __bfloat162float(in[i]);
+}
+
+__global__ void fill2_kernel(float* a, float va, float* b, float vb, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = va; b[i] = vb; }
+}
+
+// c_noise[b], c_in[b] from device sigmas (diffusion.py:235, :240)
+__global__ void precond_prepare_kernel(const float* __restrict__ sigmas, int stride, float sigma_data, float sd2,
+                                       float* __restrict__ c_noise, float* __restrict__ c_in, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        const PrecondCoef c = precond_coef(sigmas[b * stride], sigma_data, sd2);
+        c_noise[b] = c.c_noise;
+        c_in[b] = c.c_in;
+    }
+}
+
+static int check_forward_args(adb_wavenet* n, int B, int L, int precision, void* ws, int64_t ws_bytes) {
+    REQUIRE(n, "null handle");
+    REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
+    REQUIRE(precision == ADB_PRECISION_FP32 || precision == ADB_PRECISION_BF16, "unknown precision %d", precision);
+    if (precision == ADB_PRECISION_BF16 && !n->tc_ready)
+        return fail(ADB_ERR_UNSUPPORTED, "the bf16 tensor-core path is built for residual_channels == 256 (got %d)", n->C);
+    const int64_t need = adb_wavenet_workspace_bytes(n, B, L, precision);
+    REQUIRE(ws && ws_bytes >= need, "workspace too small: %lld < %lld bytes", static_cast<long long>(ws_bytes),
+            static_cast<long long>(need));
+    REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+    return ADB_OK;
+}
+
+static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, const float* in_scale, int in_scale_stride,
+                        float* out, int B, int L, int precision, const Workspace& w, float* dump_h, float* dump_skip,
+                        int dump_layers, cudaStream_t st) {
+    const int C = n->C, layers = n->layers;
+    const long long BL = static_cast<long long>(B) * L;
+    {
+        ScopedTimer t(n, ADB_TIMER_AUX, st);
+        embed_mlp_kernel<<<B, 512, 0, st>>>(c_noise, n->fc1w, n->fc1b, n->fc2w, n->fc2b, w.emb);
+        CK(cudaGetLastError());
+    }
+    if (precision == ADB_PRECISION_FP32) {
+        {
+            ScopedTimer t(n, ADB_TIMER_AUX, st);
+            embed_proj_kernel<<<dim3(B, layers), 256, 0, st>>>(w.emb, n->d_wp, n->d_bp, w.proj, B, C);
+            in_proj_kernel<false><<<grid_for(BL * (C / 8)), 256, 0, st>>>(x, in_scale, in_scale_stride, n->w_in_f, n->b_in,
+                                                                          w.hA, B, L, C);
+            CK(cudaGetLastError());
+        }
+        float *hin = w.hA, *hout = w.hB;
+        for (int l = 0; l < layers; ++l) {
+            ScopedTimer t(n, ADB_TIMER_CONV, st);
+            const LayerW& lw = n->L[l];
+            ConvF32Args a;
+            memset(&a, 0, sizeof a);
+            a.in = hin; a.padd = w.proj + static_cast<long long>(l) * B * C; a.w = lw.w1f; a.bias = lw.b1; a.out = w.y;
+            a.nb = B; a.L = L; a.Cin = C; a.Cout = 2 * C; a.taps = 3; a.dil = 1 << (l % n->cycle);
+            a.ldw = 2 * C; a.ldo = 2 * C; a.in_scale = 1.f;
+            CK(conv_cl_f32(a, st));
+            gate_f32_kernel<<<grid_for(BL * C), 256, 0, st>>>(w.y, w.z, BL, C);
+            memset(&a, 0, sizeof a);
+            a.in = w.z; a.w = lw.w2f; a.bias = lw.b2; a.out = w.o;
+            a.nb = B; a.L = L; a.Cin = C; a.Cout = 2 * C; a.taps = 1; a.dil = 1; a.ldw = 2 * C; a.ldo = 2 * C; a.in_scale = 1.f;
+            CK(conv_cl_f32(a, st));
+            res_skip_f32_kernel<<<grid_for(BL * C), 256, 0, st>>>(hin, w.o, hout, w.skip, BL, C, l == 0 ? 1 : 0);
+            CK(cudaGetLastError());
+            if (l < dump_layers) {
+                CK(cudaMemcpyAsync(dump_h + l * BL * C, hout, sizeof(float) * BL * C, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(dump_skip + l * BL * C, w.skip, sizeof(float) * BL * C, cudaMemcpyDeviceToDevice, st));
+            }
+            float* tmp = hin; hin = hout; hout = tmp;
+        }
+        {
+            ScopedTimer t(n, ADB_TIMER_CONV, st);
+            ConvF32Args a;
+            memset(&a, 0, sizeof a);
+            a.in = w.skip; a.w = n->wsp_f; a.bias = n->b_sp; a.out = w.s2;
+            a.nb = B; a.L = L; a.Cin = C; a.Cout = C; a.taps = 1; a.dil = 1; a.ldw = C; a.ldo = C;
+            a.in_scale = static_cast<float>(sqrt(1.0 / layers));      // wavenet.py:151
+            a.relu = 1;                                               // wavenet.py:178
+            CK(conv_cl_f32(a, st));
+            out_proj_f32_kernel<<<static_cast<unsigned>((BL * 32 + 255) / 256), 256, 0, st>>>(w.s2, n->w_out, n->b_out, out, BL, C);
+            CK(cudaGetLastError());
+        }
+        return ADB_OK;
+    }
+
+    // ---------------- bf16 tensor-core path ----------------
+    {
+        ScopedTimer t(n, ADB_TIMER_AUX, st);
+        ConvF32Args a;
+        memset(&a, 0, sizeof a);
+        a.in = w.emb; a.w = n->mtab; a.bias = n->cvec; a.out = w.E;
+        a.nb = 1; a.L = B; a.Cin = 512; a.Cout = layers * 1536; a.taps = 1; a.dil = 1;
+        a.ldw = static_cast<long long>(layers) * 1536; a.ldo = a.ldw; a.in_scale = 1.f;
+        CK(conv_cl_f32(a, st));
+        in_proj_kernel<true><<<grid_for(BL * (C / 8)), 256, 0, st>>>(x, in_scale, in_scale_stride, n->w_in_f, n->b_in, w.hbA,
+                                                                     B, L, C);
+        CK(cudaGetLastError());
+    }
+    int num_sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles_per_b = (L + TC_TILE_T - 1) / TC_TILE_T;
+    const int num_tiles = tiles_per_b * B;
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    __nv_bfloat16 *hin = w.hbA, *hout = w.hbB;
+    for (int l = 0; l < layers; ++l) {
+        ScopedTimer t(n, ADB_TIMER_CONV, st);
+        const CUtensorMap* tm_h = nullptr;
+        int rc = get_h_map(n, hin, B, L, &tm_h);
+        if (rc) return rc;
+        BlockTcParams bp;
+        bp.E = w.E; bp.b2 = n->L[l].b2; bp.h_in = hin; bp.h_out = hout; bp.skip = w.skip;
+        bp.B = B; bp.L = L; bp.layer = l; bp.layers = layers; bp.dil = 1 << (l % n->cycle);
+        bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
+        bp.first_layer = (l == 0); bp.write_h = (l + 1 < layers) || (l < dump_layers);
+        wavenet_block_tc_kernel<<<grid, TC_THREADS, TC_BLOCK_SMEM_BYTES, st>>>(*tm_h, n->tm_w, bp);
+        CK(cudaGetLastError());
+        if (l < dump_layers) {
+            cvt_bf16_f32_kernel<<<grid_for(BL * C), 256, 0, st>>>(hout, dump_h + l * BL * C, BL * C);
+            CK(cudaMemcpyAsync(dump_skip + l * BL * C, w.skip, sizeof(float) * BL * C, cudaMemcpyDeviceToDevice, st));
+        }
+        __nv_bfloat16* tmp = hin; hin = hout; hout = tmp;
+    }
+    {
+        ScopedTimer t(n, ADB_TIMER_CONV, st);
+        TailTcParams tp;
+        tp.skip = w.skip; tp.b_sp = n->b_sp; tp.w_out = n->w_out; tp.b_out = n->b_out; tp.out = out;
+        tp.scale = static_cast<float>(sqrt(1.0 / layers));
+        tp.B = B; tp.L = L; tp.tiles_per_b = tiles_per_b; tp.num_tiles = num_tiles;
+        wavenet_tail_tc_kernel<<<grid, 256, TC_TAIL_SMEM_BYTES, st>>>(n->tm_wsp, tp);
+        CK(cudaGetLastError());
+    }
+    return ADB_OK;
+}
+
+extern "C" int adb_wavenet_forward_debug(adb_wavenet* n, const float* x, const float* c_noise, const float* in_scale,
+                                         int in_scale_stride, float* out, int B, int L, int precision, void* ws,
+                                         int64_t ws_bytes, float* dump_h, float* dump_skip, int dump_layers, void* stream) {
+    int rc = check_forward_args(n, B, L, precision, ws, ws_bytes);
+    if (rc) return rc;
+    REQUIRE(x && c_noise && out, "null tensor argument");
+    REQUIRE(dump_layers >= 0 && dump_layers <= n->layers, "bad dump_layers");
+    REQUIRE(dump_layers == 0 || (dump_h && dump_skip), "dump buffers missing");
+    const Workspace w = carve(n, B, L, precision, ws);
+    return forward_impl(n, x, c_noise, in_scale, in_scale_stride, out, B, L, precision, w, dump_h, dump_skip, dump_layers,
+                        S(stream));
+}
+
+extern "C" int adb_wavenet_forward(adb_wavenet* n, const float* x, const float* c_noise, const float* in_scale,
+                                   int in_scale_stride, float* out, int B, int L, int precision, void* ws, int64_t ws_bytes,
+                                   void* stream) {
+    return adb_wavenet_forward_debug(n, x, c_noise, in_scale, in_scale_stride, out, B, L, precision, ws, ws_bytes, nullptr,
+                                     nullptr, 0, stream);
+}
+
+extern "C" int adb_wavenet_denoise(adb_wavenet* n, const float* x, const float* sigmas, int sigma_stride, float sigma_data,
+                                   float* out, int B, int L, int precision, void* ws, int64_t ws_bytes, void* stream) {
+    int rc = check_forward_args(n, B, L, precision, ws, ws_bytes);
+    if (rc) return rc;
+    REQUIRE(x && sigmas && out, "null tensor argument");
+    REQUIRE(sigma_stride == 0 || sigma_stride == 1, "sigma_stride must be 0 or 1");
+    const Workspace w = carve(n, B, L, precision, ws);
+    cudaStream_t st = S(stream);
+    precond_prepare_kernel<<<(B + 255) / 256, 256, 0, st>>>(sigmas, sigma_stride, sigma_data, sd2_of(sigma_data), w.c_noise,
+                                                            w.c_in, B);
+    CK(cudaGetLastError());
+    rc = forward_impl(n, x, w.c_noise, w.c_in, 1, w.fbuf, B, L, precision, w, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    return adb_edm_precond_out(x, w.fbuf, nullptr, 1.0f, sigmas, sigma_stride, sigma_data, out, B, L, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident EDM sampling trajectory
+// ------------------------------------------------------------------------------------------------
+static int net_eval(adb_wavenet* n, const float* x, float sigma, float sigma_data, float* f_out, int B, int L, int precision,
+                    const Workspace& w, cudaStream_t st) {
+    const PrecondCoef c = precond_coef(sigma, sigma_data, sd2_of(sigma_data));
+    fill2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.c_noise, c.c_noise, w.c_in, c.c_in, B);
+    CK(cudaGetLastError());
+    return forward_impl(n, x, w.c_noise, w.c_in, 1, f_out, B, L, precision, w, nullptr, nullptr, 0, st);
+}
+
+extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const float* sigmas_host, int n_sigmas,
+                                      int num_steps, float sigma_data, float s_tmin, float s_tmax, float s_churn,
+                                      float s_noise, int use_heun, float alpha, const float* eps, float* x_out, int B, int L,
+                                      int precision, void* ws, int64_t ws_bytes, int* nfe_out, void* stream) {
+    int rc = check_forward_args(n, B, L, precision, ws, ws_bytes);
+    if (rc) return rc;
+    REQUIRE(noise && sigmas_host && x_out, "null tensor argument");
+    REQUIRE(num_steps >= 1, "num_steps must be >= 1");
+    const bool alpha_mode = alpha > 0.f;
+    REQUIRE(n_sigmas >= num_steps, "schedule has %d sigmas, sampler needs %d", n_sigmas, num_steps);
+    const Workspace w = carve(n, B, L, precision, ws);
+    cudaStream_t st = S(stream);
+    const long long N = static_cast<long long>(B) * L;
+    const float sd2 = sd2_of(sigma_data);
+    int nfe = 0;
+
+    // x = sigmas[0] * noise   (sampler_edm.py:380 / :291)
+    float* x = w.xhat;
+    {
+        ScopedTimer t(n, ADB_TIMER_STEP, st);
+        rc = adb_edm_scale(noise, sigmas_host[0], x, N, stream);
+        if (rc) return rc;
+    }
+
+    if (!alpha_mode) {
+        // gamma_i = min(s_churn / N, sqrt(2) - 1) where s_tmin <= sigma_i <= s_tmax   (sampler_edm.py:383-387)
+        const float gamma_on = static_cast<float>(fmin(static_cast<double>(s_churn) / num_steps, sqrt(2.0) - 1.0));
+        if (gamma_on > 0.f) REQUIRE(eps != nullptr, "s_churn > 0 needs the churn-noise tensor eps_dev");
+        for (int i = 0; i < num_steps; ++i) {
+            const float sigma = sigmas_host[i];
+            const float sigma_next = (i + 1 < n_sigmas) ? sigmas_host[i + 1] : 0.0f;   // t_N = 0 appended (:377)
+            const float gamma = (sigma >= s_tmin && sigma <= s_tmax) ? gamma_on : 0.0f;
+            float sigma_hat = sigma;
+            if (gamma > 0.f) {
+                const float gs = gamma * sigma;
+                sigma_hat = sigma + gs;                                                    // :343
+                const float a = sqrtf(sigma_hat * sigma_hat - sigma * sigma);              // :347
+                ScopedTimer t(n, ADB_TIMER_STEP, st);
+                // x_hat = x + a * (s_noise * eps_i), each product rounded like the reference (:346-347)
+                EdmArgs p = edm_args(x, eps + static_cast<long long>(i) * N, nullptr, x, nullptr, N, N);
+                p.a = a; p.w0 = s_noise;
+                CK(edm_launch<OP_CHURN>(p, nullptr, st));
+            }
+            rc = net_eval(n, x, sigma_hat, sigma_data, w.fbuf, B, L, precision, w, st);
+            if (rc) return rc;
+            ++nfe;
+            const PrecondCoef c0 = precond_coef(sigma_hat, sigma_data, sd2);
+            const float h = sigma_next - sigma_hat;
+            EdmArgs p = edm_args(x, w.fbuf, nullptr, nullptr, nullptr, N, N);
+            p.s0 = sigma_hat; p.h = h; p.c_skip0 = c0.c_skip; p.c_out0 = c0.c_out;
+            if (sigma_next != 0.f && use_heun) {
+                {
+                    ScopedTimer t(n, ADB_TIMER_STEP, st);
+                    p.out0 = w.dslope; p.out1 = w.xnext;
+                    CK(edm_launch<OP_MID>(p, nullptr, st));
+                }
+                rc = net_eval(n, w.xnext, sigma_next, sigma_data, w.fbuf, B, L, precision, w, st);
+                if (rc) return rc;
+                ++nfe;
+                const PrecondCoef c1 = precond_coef(sigma_next, sigma_data, sd2);
+                ScopedTimer t(n, ADB_TIMER_STEP, st);
+                p.out0 = x; p.out1 = nullptr;
+                p.s1 = sigma_next; p.hh = 0.5f * h; p.c_skip1 = c1.c_skip; p.c_out1 = c1.c_out;
+                CK(edm_launch<OP_POST>(p, w.dslope, st));
+            } else {
+                ScopedTimer t(n, ADB_TIMER_STEP, st);
+                p.out0 = x;
+                CK(edm_launch<OP_EULER_RAW>(p, nullptr, st));
+            }
+        }
+    } else {
+        // EDMAlphaSampler (sampler_edm.py:251-300): num_steps - 1 iterations, no sigma = 0 appended
+        for (int i = 0; i + 1 < num_steps; ++i) {
+            const float sigma = sigmas_host[i], sigma_next = sigmas_host[i + 1];
+            const float h = sigma_next - sigma;
+            rc = net_eval(n, x, sigma, sigma_data, w.fbuf, B, L, precision, w, st);
+            if (rc) return rc;
+            ++nfe;
+            const PrecondCoef c0 = precond_coef(sigma, sigma_data, sd2);
+            const float ah = alpha * h;
+            const float sigma_p = sigma + ah;                                  // :268
+            EdmArgs p = edm_args(x, w.fbuf, nullptr, nullptr, nullptr, N, N);
+            p.s0 = sigma; p.c_skip0 = c0.c_skip; p.c_out0 = c0.c_out;
+            if (sigma_p != 0.f && use_heun) {
+                {
+                    ScopedTimer t(n, ADB_TIMER_STEP, st);
+                    p.h = ah;                                                  // x_p = x + alpha h d   (:270)
+                    p.out0 = w.dslope; p.out1 = w.xnext;
+                    CK(edm_launch<OP_MID>(p, nullptr, st));
+                }
+                rc = net_eval(n, w.xnext, sigma_p, sigma_data, w.fbuf, B, L, precision, w, st);
+                if (rc) return rc;
+                ++nfe;
+                // x_next = x + h ((1 - 1/2a) d + (1/2a) d_p)   (:271-278)
+                const PrecondCoef c1 = precond_coef(sigma_p, sigma_data, sd2);
+                ScopedTimer t(n, ADB_TIMER_STEP, st);
+                p.out0 = x; p.out1 = nullptr;
+                p.s1 = sigma_p; p.a = h; p.c_skip1 = c1.c_skip; p.c_out1 = c1.c_out;
+                p.w0 = static_cast<float>(1.0 - 0.5 / alpha); p.w1 = static_cast<float>(0.5 / alpha);
+                CK(edm_launch<OP_POST_RK2>(p, w.dslope, st));
+            } else {
+                ScopedTimer t(n, ADB_TIMER_STEP, st);
+                p.h = h;
+                p.out0 = x;
+                CK(edm_launch<OP_EULER_RAW>(p, nullptr, st));
+            }
+        }
+    }
+    if (x_out != x) CK(cudaMemcpyAsync(x_out, x, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    if (nfe_out) *nfe_out = nfe;
+    return ADB_OK;
+}

@@ -1,0 +1,243 @@
+// Fused elementwise kernels for EDM preconditioning and the Heun / Euler sampler update.
+//
+// Reference arithmetic being replaced (one fused pass instead of ~20 ATen kernels per step):
+//   EluDiffusion.get_scale_weights      src/models/components/diffusion.py:232-241
+//   Diffusion.denoise_fn (eq. 7 + clip) src/models/components/diffusion.py:46-63, utils.py:20-22
+//   EDMSampler.step                     src/models/components/sampler_edm.py:343-367
+//   EDMAlphaSampler.step                src/models/components/sampler_edm.py:259-280
+//   Diffusion.forward (DSM loss)        src/models/components/diffusion.py:76-95
+//
+// The state is fp32 [B, n] (n = C*L contiguous per sample). Every kernel is a grid-stride loop over
+// 128-bit vectors (4 floats) with a scalar tail path when n % 4 != 0 or a pointer is unaligned.
+// Rounding follows the reference's operation order (separate mul / add roundings, true division) so
+// results agree with the torch-CPU oracle to the last bit wherever libm is not involved.
+#pragma once
+#include "ptx.cuh"
+
+namespace adb {
+
+struct PrecondCoef {
+    float c_skip, c_out, c_in, c_noise;
+};
+
+// Same operation order as diffusion.py:236-240 evaluated on fp32 tensors.
+// `sd2` is (float)(double(sigma_data)^2): the reference squares the python double first and only then
+// rounds it to fp32 when it meets the fp32 tensor.
+__host__ __device__ __forceinline__ PrecondCoef precond_coef(float sigma, float sigma_data, float sd2) {
+    PrecondCoef c;
+    const float s2 = sigma * sigma;
+#ifdef __CUDA_ARCH__
+    const float sum = __fadd_rn(s2, sd2);
+    const float rs = __fdiv_rn(1.0f, __fsqrt_rn(sum));          // (..) ** -0.5 == 1/sqrt in ATen
+    c.c_skip = __fdiv_rn(sd2, sum);
+    c.c_out = __fmul_rn(__fmul_rn(sigma, sigma_data), rs);
+    c.c_in = rs;
+    c.c_noise = __fmul_rn(logf(sigma), 0.25f);
+#else
+    const float sum = s2 + sd2;
+    const float rs = 1.0f / sqrtf(sum);
+    c.c_skip = sd2 / sum;
+    c.c_out = (sigma * sigma_data) * rs;
+    c.c_in = rs;
+    c.c_noise = logf(sigma) * 0.25f;
+#endif
+    return c;
+}
+
+__device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
+
+// D = clamp(c_skip * x + c_out * F)   (diffusion.py:60,63)
+__device__ __forceinline__ float denoised(float x, float f, float c_skip, float c_out) {
+    return clamp1(__fadd_rn(__fmul_rn(c_skip, x), __fmul_rn(c_out, f)));
+}
+
+enum EdmOp : int {
+    OP_SCALE_IN = 0,     // out0 = c_in(sigma_b) * x
+    OP_COMBINE = 1,      // out0 = clamp(c_skip x + c_out F)
+    OP_COMBINE_CFG = 2,  // F = Fn + (F - Fn) * cond_scale first (diffusion.py:52-54)
+    OP_CHURN = 3,        // out0 = x + a * (w0 * eps), w0 = s_noise               (sampler_edm.py:346-347)
+    OP_EULER = 4,        // d = (x - D)/s0 ; out0 = d ; out1 = x + h d           (sampler_edm.py:354-357)
+    OP_HEUN = 5,         // d2 = (x1 - D)/s1 ; out0 = x + hh (d + d2)            (sampler_edm.py:366-367)
+    OP_RK2 = 6,          // d2 = (x1 - D)/s1 ; out0 = x + h (w0 d + w1 d2)       (sampler_edm.py:277-278)
+    OP_AXPY = 7,         // out0 = x + a * in1                                    (sampler_edm.py:280, 273)
+    OP_MID = 8,          // fused: D1 from raw F; d; x' -> out0 = d, out1 = x'
+    OP_POST = 9,         // fused: x' = x + h d; D2 from raw F; x_next -> out0
+    OP_EULER_RAW = 10,   // fused: D1 from raw F; out0 = x + h d (final Euler step / use_heun=False)
+    OP_NOISE_IN = 11,    // training: out0 = x + sigma_b * noise ; out1 = c_in(sigma_b) * out0   (diffusion.py:79,50/57)
+    OP_SCALE = 12,       // out0 = a * x                                          (sampler_edm.py:380)
+    OP_POST_RK2 = 13,    // fused general RK2: x' = x + h d; D2; out0 = x + a (w0 d + w1 d2)   (sampler_edm.py:270-278)
+};
+
+struct EdmArgs {
+    const float* x;       // primary state input
+    const float* in1;     // F / D / eps / d  (op dependent)
+    const float* in2;     // x1 / Fnull / d   (op dependent)
+    float* out0;
+    float* out1;
+    const float* sigmas;  // device sigma(s) for the per-sample ops (SCALE_IN / COMBINE* / NOISE_IN)
+    int sigma_stride;     // 0: one sigma for the whole batch, 1: sigma per sample
+    float sigma_data;
+    float sd2;            // (float)(double(sigma_data)^2)
+    float cond_scale;
+    // host scalars for the sampler ops
+    float a, s0, s1, h, hh, w0, w1, c_skip0, c_out0, c_skip1, c_out1;
+    long long n_per;      // elements per sample
+    long long total;      // B * n_per
+};
+
+// One generic kernel: loads up to 4 inputs, applies the op, stores up to 2 outputs.
+// in3 is only used by HEUN / RK2 / POST (the slope d).
+template <int OP, int VEC>
+__global__ void __launch_bounds__(256) edm_kernel(EdmArgs p, const float* __restrict__ in3) {
+    const long long nvec = p.total / VEC;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const long long base = v * VEC;
+        float cs = 0.f, co = 0.f, ci = 0.f, sg = 0.f;
+        if constexpr (OP == OP_SCALE_IN || OP == OP_COMBINE || OP == OP_COMBINE_CFG || OP == OP_NOISE_IN) {
+            const long long b = p.sigma_stride ? (base / p.n_per) : 0;
+            sg = __ldg(p.sigmas + b * p.sigma_stride);
+            const PrecondCoef c = precond_coef(sg, p.sigma_data, p.sd2);
+            cs = c.c_skip; co = c.c_out; ci = c.c_in;
+        }
+        float x[VEC], i1[VEC], i2[VEC], i3[VEC], o0[VEC], o1[VEC];
+        constexpr bool need1 = (OP != OP_SCALE_IN && OP != OP_SCALE);
+        constexpr bool need2 = (OP == OP_COMBINE_CFG || OP == OP_HEUN || OP == OP_RK2);
+        constexpr bool need3 = (OP == OP_HEUN || OP == OP_RK2 || OP == OP_POST || OP == OP_POST_RK2);
+        constexpr bool two_out = (OP == OP_EULER || OP == OP_MID || OP == OP_NOISE_IN);
+        if constexpr (VEC == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(p.x + base);
+            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+            if constexpr (need1) { const float4 u = *reinterpret_cast<const float4*>(p.in1 + base); i1[0] = u.x; i1[1] = u.y; i1[2] = u.z; i1[3] = u.w; }
+            if constexpr (need2) { const float4 u = *reinterpret_cast<const float4*>(p.in2 + base); i2[0] = u.x; i2[1] = u.y; i2[2] = u.z; i2[3] = u.w; }
+            if constexpr (need3) { const float4 u = *reinterpret_cast<const float4*>(in3 + base); i3[0] = u.x; i3[1] = u.y; i3[2] = u.z; i3[3] = u.w; }
+        } else {
+            x[0] = p.x[base];
+            if constexpr (need1) i1[0] = p.in1[base];
+            if constexpr (need2) i2[0] = p.in2[base];
+            if constexpr (need3) i3[0] = in3[base];
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            if constexpr (OP == OP_HEUN) {
+                // x = x_hat, i1 = D(x1), i2 = x1, i3 = d
+                const float d2 = __fdiv_rn(__fsub_rn(i2[k], i1[k]), p.s1);
+                o0[k] = __fadd_rn(x[k], __fmul_rn(p.hh, __fadd_rn(i3[k], d2)));
+            } else if constexpr (OP == OP_RK2) {
+                const float d2 = __fdiv_rn(__fsub_rn(i2[k], i1[k]), p.s1);
+                o0[k] = __fadd_rn(x[k], __fmul_rn(p.h, __fadd_rn(__fmul_rn(p.w0, i3[k]), __fmul_rn(p.w1, d2))));
+            } else if constexpr (OP == OP_MID) {
+                const float D = denoised(x[k], i1[k], p.c_skip0, p.c_out0);
+                const float d = __fdiv_rn(__fsub_rn(x[k], D), p.s0);
+                o0[k] = d;
+                o1[k] = __fadd_rn(x[k], __fmul_rn(p.h, d));
+            } else if constexpr (OP == OP_POST) {
+                // x = x_hat, i1 = raw F at x', i3 = d ; x' recomputed exactly as OP_MID stored it
+                const float x1 = __fadd_rn(x[k], __fmul_rn(p.h, i3[k]));
+                const float D = denoised(x1, i1[k], p.c_skip1, p.c_out1);
+                const float d2 = __fdiv_rn(__fsub_rn(x1, D), p.s1);
+                o0[k] = __fadd_rn(x[k], __fmul_rn(p.hh, __fadd_rn(i3[k], d2)));
+            } else if constexpr (OP == OP_POST_RK2) {
+                const float x1 = __fadd_rn(x[k], __fmul_rn(p.h, i3[k]));
+                const float D = denoised(x1, i1[k], p.c_skip1, p.c_out1);
+                const float d2 = __fdiv_rn(__fsub_rn(x1, D), p.s1);
+                o0[k] = __fadd_rn(x[k], __fmul_rn(p.a, __fadd_rn(__fmul_rn(p.w0, i3[k]), __fmul_rn(p.w1, d2))));
+            } else if constexpr (OP == OP_EULER_RAW) {
+                const float D = denoised(x[k], i1[k], p.c_skip0, p.c_out0);
+                const float d = __fdiv_rn(__fsub_rn(x[k], D), p.s0);
+                o0[k] = __fadd_rn(x[k], __fmul_rn(p.h, d));
+            } else if constexpr (OP == OP_NOISE_IN) {
+                const float xn = __fadd_rn(x[k], __fmul_rn(sg, i1[k]));
+                o0[k] = xn;
+                o1[k] = __fmul_rn(ci, xn);
+            } else if constexpr (OP == OP_SCALE_IN) {
+                o0[k] = __fmul_rn(ci, x[k]);
+            } else if constexpr (OP == OP_COMBINE) {
+                o0[k] = denoised(x[k], i1[k], cs, co);
+            } else if constexpr (OP == OP_COMBINE_CFG) {
+                // i1 = F(cond), i2 = F(null): null + (cond - null) * scale   (diffusion.py:54)
+                const float f = __fadd_rn(i2[k], __fmul_rn(__fsub_rn(i1[k], i2[k]), p.cond_scale));
+                o0[k] = denoised(x[k], f, cs, co);
+            } else if constexpr (OP == OP_CHURN) {
+                o0[k] = __fadd_rn(x[k], __fmul_rn(p.a, __fmul_rn(p.w0, i1[k])));
+            } else if constexpr (OP == OP_AXPY) {
+                o0[k] = __fadd_rn(x[k], __fmul_rn(p.a, i1[k]));
+            } else if constexpr (OP == OP_EULER) {
+                const float d = __fdiv_rn(__fsub_rn(x[k], i1[k]), p.s0);
+                o0[k] = d;
+                o1[k] = __fadd_rn(x[k], __fmul_rn(p.h, d));
+            } else if constexpr (OP == OP_SCALE) {
+                o0[k] = __fmul_rn(p.a, x[k]);
+            }
+        }
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<float4*>(p.out0 + base) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+            if constexpr (two_out) *reinterpret_cast<float4*>(p.out1 + base) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+        } else {
+            p.out0[base] = o0[0];
+            if constexpr (two_out) p.out1[base] = o1[0];
+        }
+    }
+}
+
+// c_noise[b] = 0.25 * ln(sigma_b)  (diffusion.py:235) — B values, one tiny launch.
+__global__ void edm_cnoise_kernel(const float* __restrict__ sigmas, int sigma_stride, float* __restrict__ c_noise,
+                                  int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) c_noise[b] = __fmul_rn(logf(sigmas[b * sigma_stride]), 0.25f);
+}
+
+// DSM loss (diffusion.py:92-95): loss_b = lambda(sigma_b) * sum_i (D_i - x_i)^2 / n, with
+// D = clamp(c_skip x_noisy + c_out F). One block per (sample, chunk); per-sample atomics finish it.
+__global__ void __launch_bounds__(256) edm_dsm_loss_kernel(const float* __restrict__ x, const float* __restrict__ x_noisy,
+                                                           const float* __restrict__ F, const float* __restrict__ sigmas,
+                                                           float sigma_data, float sd2, float* __restrict__ loss,
+                                                           long long n_per, int chunks) {
+    const int b = blockIdx.x / chunks;
+    const int ch = blockIdx.x % chunks;
+    const float sg = sigmas[b];
+    const PrecondCoef c = precond_coef(sg, sigma_data, sd2);
+    const long long per = (n_per + chunks - 1) / chunks;
+    const long long lo = ch * per;
+    const long long hi = (lo + per < n_per) ? lo + per : n_per;
+    float acc = 0.f;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const long long g = b * n_per + i;
+        const float D = denoised(x_noisy[g], F[g], c.c_skip, c.c_out);
+        const float e = D - x[g];
+        acc = fmaf(e, e, acc);
+    }
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        acc = red[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffu, acc, o);
+        if (threadIdx.x == 0) {
+            // lambda(sigma) = (s^2 + sd^2) * (s*sd)^-2   (diffusion.py:245)
+            const float sd = sigma_data;
+            const float w = (sg * sg + sd2) / ((sg * sd) * (sg * sd));
+            atomicAdd(loss + b, acc * w / static_cast<float>(n_per));
+        }
+    }
+}
+
+template <int OP>
+inline cudaError_t edm_launch(const EdmArgs& p, const float* in3, cudaStream_t stream) {
+    if (p.total <= 0) return cudaSuccess;
+    auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec = (p.n_per % 4 == 0) && aligned(p.x) && aligned(p.in1) && aligned(p.in2) && aligned(p.out0) &&
+                     aligned(p.out1) && aligned(in3);
+    const long long work = vec ? p.total / 4 : p.total;
+    long long blocks = (work + 255) / 256;
+    const long long cap = 148LL * 16;      // 16 resident 256-thread CTAs per SM's worth of grid-stride
+    if (blocks > cap) blocks = cap;
+    if (vec) edm_kernel<OP, 4><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p, in3);
+    else     edm_kernel<OP, 1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p, in3);
+    return cudaGetLastError();
+}
+
+}  // namespace adb

@@ -1,0 +1,140 @@
+/*
+ * adb200 — C ABI of the B200-native EDM sampling / denoising hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no framework types. Every pointer named
+ * `*_dev` / documented "device" is a CUDA device pointer on the current device; `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = default stream). All functions enqueue asynchronously on
+ * `stream`, never synchronise unless stated, and return 0 on success or a non-zero code, in which
+ * case `adb_last_error()` holds a message. There is no CPU fallback: on a device that is not
+ * sm_100 every compute entry point fails.
+ *
+ * Each entry point names the reference code (AgentCooper2002/AudioDiffuser, paths relative to the
+ * reference root) whose arithmetic it replaces. INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ */
+#ifndef ADB200_H
+#define ADB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADB_OK 0
+#define ADB_ERR_INVALID 1      /* bad argument (shape, alignment, NULL) */
+#define ADB_ERR_CUDA 2         /* CUDA runtime / driver error */
+#define ADB_ERR_UNSUPPORTED 3  /* option outside the fused path (caller must not silently fall back) */
+#define ADB_ERR_PIPELINE 4     /* an in-kernel barrier wait timed out (programming error, reported by adb_check_async) */
+
+#define ADB_PRECISION_FP32 0   /* CUDA-core fp32 path: <= 1e-5 relative to the reference */
+#define ADB_PRECISION_BF16 1   /* tcgen05 path: bf16 operands, fp32 accumulate: <= 2e-2 relative */
+
+const char* adb_last_error(void);
+int adb_version(void);
+/* 0 if `device` is sm_100 (B200) and usable. */
+int adb_device_check(int device);
+/* Synchronise the device and report any asynchronous kernel / pipeline error (test & bench use). */
+int adb_check_async(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * EDM preconditioning — src/models/components/diffusion.py:232-241 (get_scale_weights) and :46-63
+ * (denoise_fn). State tensors are fp32, contiguous, `n_per` elements per sample, `B` samples.
+ * `sigmas_dev` holds 1 value (sigma_stride = 0, the sampler's scalar sigma, utils.py:41-52) or B
+ * values (sigma_stride = 1, training).
+ * ---------------------------------------------------------------------------------------------- */
+/* net_in = c_in(sigma) * x ; c_noise[b] = 0.25 ln(sigma_b)   (diffusion.py:50, :235) */
+int adb_edm_precond_in(const float* x_dev, const float* sigmas_dev, int sigma_stride, float sigma_data,
+                       float* net_in_dev, float* c_noise_dev, int B, int64_t n_per, void* stream);
+/* out = clamp(c_skip x + c_out F, -1, 1)   (diffusion.py:60-63; dynamic_threshold == 0 only).
+ * If f_null_dev != NULL: F = f_null + (f - f_null) * cond_scale first (diffusion.py:52-54). */
+int adb_edm_precond_out(const float* x_dev, const float* f_dev, const float* f_null_dev, float cond_scale,
+                        const float* sigmas_dev, int sigma_stride, float sigma_data, float* out_dev, int B,
+                        int64_t n_per, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler updates on a denoised estimate D (generic path: any `fn`) —
+ * src/models/components/sampler_edm.py:343-367 (EDMSampler.step), :259-280 (EDMAlphaSampler.step).
+ * ---------------------------------------------------------------------------------------------- */
+/* out = a * x            (sampler_edm.py:380  x = sigmas[0] * noise) */
+int adb_edm_scale(const float* x_dev, float a, float* out_dev, int64_t n, void* stream);
+/* out = x + a * e        (churn: sampler_edm.py:347 with a = sqrt(sigma_hat^2 - sigma^2) * s_noise; also :273, :280) */
+int adb_edm_axpy(const float* x_dev, const float* e_dev, float a, float* out_dev, int64_t n, void* stream);
+/* d = (x - D) / sigma ; x_next = x + h d          (sampler_edm.py:354-357) */
+int adb_edm_euler(const float* x_dev, const float* denoised_dev, float sigma, float h, float* d_dev,
+                  float* x_next_dev, int64_t n, void* stream);
+/* d2 = (x1 - D1) / sigma1 ; out = x + h (w0 d + w1 d2)   (Heun: w0 = w1 = 0.5, sampler_edm.py:366-367;
+ * general RK2: w0 = 1 - 1/(2 alpha), w1 = 1/(2 alpha), sampler_edm.py:277-278) */
+int adb_edm_rk2(const float* x_dev, const float* d_dev, const float* x1_dev, const float* denoised1_dev,
+                float sigma1, float h, float w0, float w1, float* out_dev, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training twin — src/models/components/diffusion.py:65-97 (Diffusion.forward).
+ * ---------------------------------------------------------------------------------------------- */
+/* x_noisy = x + sigma_b * noise ; net_in = c_in(sigma_b) * x_noisy ; c_noise[b]   (diffusion.py:79, :57) */
+int adb_edm_noise_in(const float* x_dev, const float* noise_dev, const float* sigmas_dev, float sigma_data,
+                     float* x_noisy_dev, float* net_in_dev, float* c_noise_dev, int B, int64_t n_per, void* stream);
+/* loss[b] = lambda(sigma_b) * mean_i (clamp(c_skip x_noisy + c_out F) - x)^2   (diffusion.py:60-63, :92-95) */
+int adb_edm_dsm_loss(const float* x_dev, const float* x_noisy_dev, const float* f_dev, const float* sigmas_dev,
+                     float sigma_data, float* loss_dev, int B, int64_t n_per, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DiffWave backbone — src/models/backbones/wavenet.py:153-180 (WaveNetNoise), :117-151, :94-115.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct adb_wavenet adb_wavenet;
+
+/* Number of fp32 values of the flat parameter vector for a given configuration: the concatenation
+ * of WaveNetNoise(...).state_dict() values in state_dict order (wavenet.py:153-168). */
+int64_t adb_wavenet_param_count(int residual_channels, int residual_layers);
+/* Create from the flat parameter vector (device or host pointer; `on_device` says which). Folds the
+ * weight norm (wavenet.py:44-51), packs weights for both precisions. Synchronises. */
+int adb_wavenet_create(adb_wavenet** out, int residual_channels, int residual_layers, int dilation_cycle,
+                       const float* params, int64_t n_params, int on_device);
+void adb_wavenet_destroy(adb_wavenet* net);
+/* Bytes of scratch the calls below need for (B, L, precision); the caller owns the buffer. */
+int64_t adb_wavenet_workspace_bytes(const adb_wavenet* net, int B, int L, int precision);
+
+/* F = WaveNetNoise(in_scale_b * x, c_noise)   (wavenet.py:170-180): x [B][L] -> out [B][L] (the
+ * reference's [B,1,L]). `in_scale_dev` may be NULL (scale 1); stride 0 = one value for the batch. */
+int adb_wavenet_forward(adb_wavenet* net, const float* x_dev, const float* c_noise_dev, const float* in_scale_dev,
+                        int in_scale_stride, float* out_dev, int B, int L, int precision, void* workspace_dev,
+                        int64_t workspace_bytes, void* stream);
+/* Same, additionally copying h and the running skip sum after each of the first `dump_layers`
+ * residual blocks into fp32 [dump_layers][B][L][C] buffers (debug / unit tests). */
+int adb_wavenet_forward_debug(adb_wavenet* net, const float* x_dev, const float* c_noise_dev,
+                              const float* in_scale_dev, int in_scale_stride, float* out_dev, int B, int L,
+                              int precision, void* workspace_dev, int64_t workspace_bytes, float* dump_h_dev,
+                              float* dump_skip_dev, int dump_layers, void* stream);
+/* x0_hat = EluDiffusion.denoise_fn(x, net, sigma | sigmas)  fused with the backbone
+ * (diffusion.py:32-63 + wavenet.py:170-180). */
+int adb_wavenet_denoise(adb_wavenet* net, const float* x_dev, const float* sigmas_dev, int sigma_stride,
+                        float sigma_data, float* out_dev, int B, int L, int precision, void* workspace_dev,
+                        int64_t workspace_bytes, void* stream);
+
+/* Whole EDM sampling trajectory on the device — EDMSampler.forward (sampler_edm.py:371-397) when
+ * alpha < 0, EDMAlphaSampler.forward (sampler_edm.py:284-300) when alpha > 0.
+ *   sigmas_host [n_sigmas]  the schedule (fp32, host), e.g. KarrasSchedule (scheduler.py:17-22)
+ *   eps_dev                 churn noise, [num_steps][B][L] N(0,1) fp32, or NULL when s_churn == 0
+ *                           (EDMSampler draws it every step, sampler_edm.py:346; only steps with
+ *                            gamma > 0 read it)
+ * Writes x [B][L] and, if nfe_out != NULL, the number of network evaluations. */
+int adb_wavenet_sample_edm(adb_wavenet* net, const float* noise_dev, const float* sigmas_host, int n_sigmas,
+                           int num_steps, float sigma_data, float s_tmin, float s_tmax, float s_churn, float s_noise,
+                           int use_heun, float alpha, const float* eps_dev, float* x_out_dev, int B, int L,
+                           int precision, void* workspace_dev, int64_t workspace_bytes, int* nfe_out, void* stream);
+
+/* Per-kernel-class device time of the last *_timed call below (microseconds, CUDA events). */
+#define ADB_TIMER_CONV 0   /* residual-block kernels (+ tail GEMM) */
+#define ADB_TIMER_STEP 1   /* fused sampler-step kernels */
+#define ADB_TIMER_AUX 2    /* embedding MLP / E table / input projection */
+#define ADB_TIMER_COUNT 3
+/* Enable (1) / disable (0) event timing around kernel classes inside adb_wavenet_sample_edm and
+ * adb_wavenet_forward; adb_wavenet_timers() synchronises and returns accumulated ms and launch counts. */
+int adb_wavenet_set_timing(adb_wavenet* net, int enabled);
+int adb_wavenet_timers(adb_wavenet* net, double* ms_out /*[ADB_TIMER_COUNT]*/, int64_t* launches_out /*[ADB_TIMER_COUNT]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADB200_H */
