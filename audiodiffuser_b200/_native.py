@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libadb200.so")
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16}
-TIMER_NAMES = ("conv", "step", "aux")
+TIMER_NAMES = ("conv", "step", "aux", "tail")
 
 _lib = None
 

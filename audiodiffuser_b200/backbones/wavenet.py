@@ -221,8 +221,8 @@ class WaveNetNoise(nn.Module):
         N.check(N.lib().adb_wavenet_set_timing(self._native(), int(enabled)))
 
     def timers(self):
-        ms = (ctypes.c_double * 3)()
-        cnt = (c_int64 * 3)()
+        ms = (ctypes.c_double * len(N.TIMER_NAMES))()
+        cnt = (c_int64 * len(N.TIMER_NAMES))()
         N.check(N.lib().adb_wavenet_timers(self._native(), ms, cnt))
         return {n: (ms[i], cnt[i]) for i, n in enumerate(N.TIMER_NAMES)}
 

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -215,7 +216,7 @@ struct TimerPair {
 
 struct HMap {
     const void* ptr;
-    int B, L;
+    int B, L, kind;
     CUtensorMap map;
 };
 
@@ -241,8 +242,8 @@ struct adb_wavenet {
     bool timing = false;
     std::vector<TimerPair> timers;
     size_t timers_used = 0;
-    double ms_acc[ADB_TIMER_COUNT] = {0, 0, 0};
-    int64_t launches[ADB_TIMER_COUNT] = {0, 0, 0};
+    double ms_acc[ADB_TIMER_COUNT] = {0, 0, 0, 0};
+    int64_t launches[ADB_TIMER_COUNT] = {0, 0, 0, 0};
     std::vector<void*> owned;
 };
 
@@ -250,8 +251,8 @@ struct ScopedTimer {
     adb_wavenet* n;
     cudaStream_t s;
     int idx = -1;
-    ScopedTimer(adb_wavenet* net, int cls, cudaStream_t st) : n(net), s(st) {
-        n->launches[cls]++;
+    ScopedTimer(adb_wavenet* net, int cls, cudaStream_t st, int nlaunch = 1) : n(net), s(st) {
+        n->launches[cls] += nlaunch;
         if (!n->timing) return;
         if (n->timers_used == n->timers.size()) {
             TimerPair t;
@@ -323,32 +324,36 @@ static int make_weight_map(CUtensorMap* map, const void* base, uint64_t rows) {
     return ADB_OK;
 }
 
-// 3-D map over channels-last activations [B][L][256] bf16, box [64 ch][128 t][1]; out-of-range time
-// coordinates (negative or >= L) are zero-filled, which is the convolution's zero padding.
-static int make_h_map(CUtensorMap* map, const void* base, int B, int L) {
+// 3-D maps over channels-last activations [B][L][256].
+//   kind 0: bf16 load map, box [64 ch][128 t][1] — out-of-range time coordinates (negative or >= L) are
+//           zero-filled, which is the convolution's zero padding;
+//   kind 1: bf16 store map, box [64 ch][32 t][1]; kind 2: fp32 store / reduce map, box [32 ch][32 t][1].
+static int make_act_map(CUtensorMap* map, const void* base, int B, int L, int kind) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const bool f32 = (kind == 2);
+    const cuuint64_t esz = f32 ? 4 : 2;
     cuuint64_t dims[3] = {256, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
-    cuuint64_t strides[2] = {512, static_cast<cuuint64_t>(L) * 512};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint64_t strides[2] = {256 * esz, static_cast<cuuint64_t>(L) * 256 * esz};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, kind == 0 ? 128u : 32u, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled(h) failed: %d", static_cast<int>(r));
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled(act kind %d) failed: %d", kind, static_cast<int>(r));
     return ADB_OK;
 }
 
-static int get_h_map(adb_wavenet* n, const void* ptr, int B, int L, const CUtensorMap** out) {
+static int get_act_map(adb_wavenet* n, const void* ptr, int B, int L, int kind, CUtensorMap* out) {
     for (auto& m : n->hmaps)
-        if (m.ptr == ptr && m.B == B && m.L == L) { *out = &m.map; return ADB_OK; }
+        if (m.ptr == ptr && m.B == B && m.L == L && m.kind == kind) { *out = m.map; return ADB_OK; }
     if (n->hmaps.size() > 64) n->hmaps.clear();
     HMap m;
-    m.ptr = ptr; m.B = B; m.L = L;
-    int rc = make_h_map(&m.map, ptr, B, L);
+    m.ptr = ptr; m.B = B; m.L = L; m.kind = kind;
+    int rc = make_act_map(&m.map, ptr, B, L, kind);
     if (rc) return rc;
     n->hmaps.push_back(m);
-    *out = &n->hmaps.back().map;
+    *out = m.map;
     return ADB_OK;
 }
 
@@ -381,12 +386,38 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             return fail(ADB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
         }                                                                                           \
     } while (0)
-    CKN(dmalloc(n, &n->params, n_params));
-    CKN(cudaMemcpy(n->params, params, sizeof(float) * n_params, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-
-    // ---- carve the flat vector in state_dict order (wavenet.py:153-168) ----
-    const float* p = n->params;
-    auto take = [&](int64_t cnt) { const float* r = p; p += cnt; return r; };
+    // ---- carve the flat vector in state_dict order (wavenet.py:153-168) into a copy whose tensors
+    //      each start on a 256-byte boundary (the kernels use 128-bit loads on them) ----
+    std::vector<int64_t> counts;
+    counts.insert(counts.end(), {C, 1, C, 512 * 128, 512, 512 * 512, 512});
+    for (int l = 0; l < layers; ++l)
+        counts.insert(counts.end(), {2 * C, 1, 2LL * C * C * 3, C * 512LL, C, 2 * C, 1, 2LL * C * C});
+    counts.insert(counts.end(), {C, 1, static_cast<int64_t>(C) * C, C, 1});
+    std::vector<int64_t> dst_off(counts.size());
+    int64_t padded = 0, src_total = 0;
+    for (size_t i = 0; i < counts.size(); ++i) {
+        dst_off[i] = padded;
+        padded += (counts[i] + 63) / 64 * 64;
+        src_total += counts[i];
+    }
+    if (src_total != n_params) { adb_wavenet_destroy(n); return fail(ADB_ERR_INVALID, "internal: parameter carve mismatch"); }
+    CKN(dmalloc(n, &n->params, static_cast<size_t>(padded)));
+    CKN(cudaMemset(n->params, 0, sizeof(float) * padded));
+    {
+        int64_t src_off = 0;
+        for (size_t i = 0; i < counts.size(); ++i) {
+            CKN(cudaMemcpy(n->params + dst_off[i], params + src_off, sizeof(float) * counts[i],
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+            src_off += counts[i];
+        }
+    }
+    size_t piece = 0;
+    auto take = [&](int64_t cnt) {
+        const float* r = n->params + dst_off[piece];
+        (void)cnt;
+        ++piece;
+        return r;
+    };
     n->b_in = take(C); n->g_in = take(1); n->v_in = take(C);
     n->fc1w = take(512 * 128); n->fc1b = take(512); n->fc2w = take(512 * 512); n->fc2b = take(512);
     n->L.resize(layers);
@@ -398,7 +429,6 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     }
     n->b_sp = take(C); n->g_sp = take(1); n->v_sp = take(static_cast<int64_t>(C) * C);
     n->w_out = take(C); n->b_out = take(1);
-    if (p - n->params != n_params) { adb_wavenet_destroy(n); return fail(ADB_ERR_INVALID, "internal: parameter carve mismatch"); }
 
     // ---- weight-norm scales: one block per weight-normed conv ----
     const int njobs = 2 * layers + 2;
@@ -591,7 +621,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     }
     if (precision == ADB_PRECISION_FP32) {
         {
-            ScopedTimer t(n, ADB_TIMER_AUX, st);
+            ScopedTimer t(n, ADB_TIMER_AUX, st, 2);
             embed_proj_kernel<<<dim3(B, layers), 256, 0, st>>>(w.emb, n->d_wp, n->d_bp, w.proj, B, C);
             in_proj_kernel<false><<<grid_for(BL * (C / 8)), 256, 0, st>>>(x, in_scale, in_scale_stride, n->w_in_f, n->b_in,
                                                                           w.hA, B, L, C);
@@ -599,7 +629,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
         }
         float *hin = w.hA, *hout = w.hB;
         for (int l = 0; l < layers; ++l) {
-            ScopedTimer t(n, ADB_TIMER_CONV, st);
+            ScopedTimer t(n, ADB_TIMER_CONV, st, 4);
             const LayerW& lw = n->L[l];
             ConvF32Args a;
             memset(&a, 0, sizeof a);
@@ -621,7 +651,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
             float* tmp = hin; hin = hout; hout = tmp;
         }
         {
-            ScopedTimer t(n, ADB_TIMER_CONV, st);
+            ScopedTimer t(n, ADB_TIMER_TAIL, st, 2);
             ConvF32Args a;
             memset(&a, 0, sizeof a);
             a.in = w.skip; a.w = n->wsp_f; a.bias = n->b_sp; a.out = w.s2;
@@ -637,7 +667,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
 
     // ---------------- bf16 tensor-core path ----------------
     {
-        ScopedTimer t(n, ADB_TIMER_AUX, st);
+        ScopedTimer t(n, ADB_TIMER_AUX, st, 2);
         ConvF32Args a;
         memset(&a, 0, sizeof a);
         a.in = w.emb; a.w = n->mtab; a.bias = n->cvec; a.out = w.E;
@@ -660,15 +690,18 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     __nv_bfloat16 *hin = w.hbA, *hout = w.hbB;
     for (int l = 0; l < layers; ++l) {
         ScopedTimer t(n, ADB_TIMER_CONV, st);
-        const CUtensorMap* tm_h = nullptr;
-        int rc = get_h_map(n, hin, B, L, &tm_h);
+        CUtensorMap m_h, m_hout, m_skip;
+        int rc = get_act_map(n, hin, B, L, 0, &m_h);
+        if (!rc) rc = get_act_map(n, hout, B, L, 1, &m_hout);
+        if (!rc) rc = get_act_map(n, w.skip, B, L, 2, &m_skip);
         if (rc) return rc;
         BlockTcParams bp;
         bp.E = w.E; bp.b2 = n->L[l].b2; bp.h_in = hin; bp.h_out = hout; bp.skip = w.skip;
         bp.B = B; bp.L = L; bp.layer = l; bp.layers = layers; bp.dil = 1 << (l % n->cycle);
         bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
         bp.first_layer = (l == 0); bp.write_h = (l + 1 < layers) || (l < dump_layers);
-        wavenet_block_tc_kernel<<<grid, TC_THREADS, TC_BLOCK_SMEM_BYTES, st>>>(*tm_h, n->tm_w, bp);
+        { const char* e = getenv("ADB_DEBUG_FLAGS"); bp.dbg = e ? atoi(e) : 0; }
+        wavenet_block_tc_kernel<<<grid, TC_THREADS, TC_BLOCK_SMEM_BYTES, st>>>(m_h, n->tm_w, m_hout, m_skip, bp);
         CK(cudaGetLastError());
         if (l < dump_layers) {
             cvt_bf16_f32_kernel<<<grid_for(BL * C), 256, 0, st>>>(hout, dump_h + l * BL * C, BL * C);
@@ -677,7 +710,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
         __nv_bfloat16* tmp = hin; hin = hout; hout = tmp;
     }
     {
-        ScopedTimer t(n, ADB_TIMER_CONV, st);
+        ScopedTimer t(n, ADB_TIMER_TAIL, st);
         TailTcParams tp;
         tp.skip = w.skip; tp.b_sp = n->b_sp; tp.w_out = n->w_out; tp.b_out = n->b_out; tp.out = out;
         tp.scale = static_cast<float>(sqrt(1.0 / layers));
@@ -732,6 +765,7 @@ static int net_eval(adb_wavenet* n, const float* x, float sigma, float sigma_dat
     const PrecondCoef c = precond_coef(sigma, sigma_data, sd2_of(sigma_data));
     fill2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.c_noise, c.c_noise, w.c_in, c.c_in, B);
     CK(cudaGetLastError());
+    n->launches[ADB_TIMER_AUX]++;
     return forward_impl(n, x, w.c_noise, w.c_in, 1, f_out, B, L, precision, w, nullptr, nullptr, 0, st);
 }
 

@@ -117,6 +117,25 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
         : "memory");
 }
 
+// smem -> global tensor stores (bulk async group). Rows outside the tensor are clipped by hardware.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// smem -> global element-wise += (performed at L2; no read comes back to the SM)
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have their shared-memory READS pending
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ---- TMEM allocation ------------------------------------------------------------------------------
 // Must be executed by one full warp; the same warp deallocates.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {

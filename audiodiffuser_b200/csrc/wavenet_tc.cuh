@@ -7,6 +7,12 @@
 //   GEMM2 (1x1 conv, K = 256): o = W2 * z                                                   (wavenet.py:113)
 //   epilogue 2: h' = (h + o[:256] + b) / sqrt(2) -> bf16 ; skip += o[256:] + b (fp32)        (wavenet.py:114-115,149)
 //
+// Epilogue 2 never loads from global memory: the residual input h is added inside the tensor core
+// (four extra N = 64 MMAs per tile multiply the centre-tap activation tile by a 64 x 64 identity, which
+// is exact in fp32), and the skip sum is updated with a TMA reduce-add performed at L2. Outputs are
+// transposed through shared memory (the z buffer, idle once GEMM2 has finished) and leave as TMA
+// tensor stores, so every global transaction is a full 128-byte row segment.
+//
 // Data layout: activations channels-last bf16 [B][L][256], so both MMA operands are K-major and a
 // dilated tap is a row offset of +-d in a 3-D TMA tensor map whose out-of-bounds zero fill IS the
 // convolution's zero padding (wavenet.py:71). Weights are pre-packed (api.cu) into 32 KB blocks
@@ -47,10 +53,12 @@ struct BlockTcSmem {
     static constexpr int z = TC_STAGES * TC_STAGE_BYTES;
     static constexpr int evec = z + TC_Z_BYTES;                 // 3 x 512 fp32
     static constexpr int b2 = evec + 3 * 512 * 4;               // 512 fp32
-    static constexpr int bars = b2 + 512 * 4;                   // mbarriers
+    static constexpr int ident = b2 + 512 * 4;                  // [64 n][64 k] bf16 identity, K-major SW128 (8 KB)
+    static constexpr int bars = ident + 64 * 128;               // mbarriers
     static constexpr int tmem_ptr = bars + 16 * 8;
     static constexpr int total = tmem_ptr + 16;
 };
+static_assert(BlockTcSmem::ident % 1024 == 0, "identity tile must sit on a swizzle-atom boundary");
 constexpr int TC_BLOCK_SMEM_BYTES = BlockTcSmem::total + 1024;  // + alignment slack
 
 struct BlockTcParams {
@@ -63,6 +71,7 @@ struct BlockTcParams {
     int tiles_per_b, num_tiles;
     int first_layer;                // 1: skip = value, 0: skip += value
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
+    int dbg;                        // debug bits (ADB_DEBUG_FLAGS): 1 = skip epilogue-2 global memory traffic
 };
 
 enum TcWaitSite : uint32_t {
@@ -76,6 +85,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
+                        const __grid_constant__ CUtensorMap tm_hout, const __grid_constant__ CUtensorMap tm_skip,
                         const BlockTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -95,6 +105,8 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_h);
         tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_hout);
+        tma_prefetch_desc(&tm_skip);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -112,12 +124,26 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     }
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < 512; i += TC_EPI_THREADS) s_b2[i] = p.b2[i];
+        // identity operand: element (n, k) lives in 16-byte chunk (k / 8) ^ (n & 7) of row n
+        uint4* id4 = reinterpret_cast<uint4*>(smem + BlockTcSmem::ident);
+        for (int i = threadIdx.x - 64; i < 64 * 8; i += TC_EPI_THREADS) {
+            const int n = i >> 3, phys = i & 7;
+            const int chunk = phys ^ (n & 7);                  // logical chunk stored at this position
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (chunk == (n >> 3)) {
+                const int e = n & 7;                           // element inside the chunk
+                w[e >> 1] = (e & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+            }
+            id4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async_smem();
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
     constexpr uint32_t IDESC = umma_idesc_bf16_f32(128, 256);
+    constexpr uint32_t IDESC_N64 = umma_idesc_bf16_f32(128, 64);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -139,6 +165,10 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                             mbar_arrive_expect_tx(&bar_full[stage], TC_STAGE_BYTES);
                             const int tap = kb >> 2, cib = kb & 3;
                             tma_load_3d(sa, &tm_h, &bar_full[stage], cib * 64, t0 + (tap - 1) * p.dil, b);
+                        } else if (job == 2) {
+                            // residual job: also fetch h[t0.., 64 kb .. 64 kb + 63] for the identity MMA
+                            mbar_arrive_expect_tx(&bar_full[stage], TC_STAGE_BYTES);
+                            tma_load_3d(sa, &tm_h, &bar_full[stage], kb * 64, t0, b);
                         } else {
                             mbar_arrive_expect_tx(&bar_full[stage], TC_B_BYTES);
                         }
@@ -180,6 +210,14 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                             umma_bf16_ss(d_tmem, umma_desc_sw128_kmajor(a_addr + k * 32),
                                          umma_desc_sw128_kmajor(b_addr + k * 32), IDESC, (kb | k) != 0 ? 1u : 0u);
                         }
+                        if (job == 2) {
+                            // + h: D[:, 64 kb .. 64 kb + 63] += h_tile * I   (exact: bf16 x 1.0 in fp32)
+                            const uint32_t id_addr = smem_u32(smem + BlockTcSmem::ident);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_ss(d_tmem + kb * 64, umma_desc_sw128_kmajor(sa + k * 32),
+                                             umma_desc_sw128_kmajor(id_addr + k * 32), IDESC_N64, 1u);
+                        }
                         umma_commit(&bar_empty[stage]);
                         if (kb == nkb - 1) umma_commit(&bar_tfull[buf]);
                     }
@@ -205,7 +243,6 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             const int b = tile / p.tiles_per_b;
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
             const int t = t0 + row;
-            const bool valid = t < p.L;
             named_bar_sync(1, TC_EPI_THREADS);
             {
                 const float* src = p.E + (static_cast<long long>(b) * p.layers + p.layer) * 1536;
@@ -265,34 +302,43 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 }
             }
 
-            // ---- epilogue 2r: residual half -> h_out (bf16) ----
+            // ---- epilogue 2: both GEMM2 halves, after the skip half (the last MMAs reading z) has finished.
+            //      Each warp owns 8 KB of the idle z buffer as two 4 KB transposition boxes (32 rows x 128 B,
+            //      128-byte swizzle) that leave through TMA.
+            mbar_wait(&bar_tfull[1], use1 & 1, SITE_EPI_TFULL, 3);
+            ++use1;
+            uint8_t* stg = zbase + ew * 8192;
+            const int trow = t0 + q * 32;                 // first time step of this warp's 32 rows
             if (p.write_h) {
                 mbar_wait(&bar_tfull[0], use0 & 1, SITE_EPI_TFULL, 2);
                 ++use0;
                 tc_fence_after_sync();
-                const long long rowoff = (static_cast<long long>(b) * p.L + t) * TC_C;
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int col = half * 128 + cc * 32;
+                    const int col = half * 128 + cc * 32;     // residual channel of r[0]
                     uint32_t r[32];
                     tmem_ld_32x32(t_lane + col, r);
                     tmem_ld_wait();
-                    if (valid) {
-                        const uint4* hin = reinterpret_cast<const uint4*>(p.h_in + rowoff + col);
-                        uint4* hout = reinterpret_cast<uint4*>(p.h_out + rowoff + col);
+                    uint32_t pk[16];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const uint4 hv = hin[m];
-                            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-                            uint32_t ow[4];
+                    for (int i = 0; i < 32; i += 2) {
+                        const float v0 = (__uint_as_float(r[i]) + s_b2[col + i]) * 0.70710678118654752f;
+                        const float v1 = (__uint_as_float(r[i + 1]) + s_b2[col + i + 1]) * 0.70710678118654752f;
+                        pk[i >> 1] = pack_bf16x2(v0, v1);
+                    }
+                    // box (cc >> 1) holds 64 channels; this chunk is its 16-byte chunks 4 (cc & 1) .. + 3
+                    uint8_t* brow = stg + (cc >> 1) * 4096 + lane * 128;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = m * 8 + u * 2;
-                                const float v0 = (bf16_lo(hw[u]) + (__uint_as_float(r[i]) + s_b2[col + i])) * 0.70710678118654752f;
-                                const float v1 = (bf16_hi(hw[u]) + (__uint_as_float(r[i + 1]) + s_b2[col + i + 1])) * 0.70710678118654752f;
-                                ow[u] = pack_bf16x2(v0, v1);
-                            }
-                            hout[m] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    for (int m = 0; m < 4; ++m) {
+                        const int chunk = (4 * (cc & 1) + m) ^ (lane & 7);
+                        *reinterpret_cast<uint4*>(brow + chunk * 16) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+                    }
+                    if (cc & 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && !(p.dbg & 1)) {
+                            tma_store_3d(&tm_hout, stg + (cc >> 1) * 4096, half * 128 + (cc >> 1) * 64, trow, b);
+                            tma_store_commit();
                         }
                     }
                 }
@@ -300,41 +346,46 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[0]);
             }
-
-            // ---- epilogue 2s: skip half -> fp32 running sum ----
             {
-                mbar_wait(&bar_tfull[1], use1 & 1, SITE_EPI_TFULL, 3);
-                ++use1;
                 tc_fence_after_sync();
-                const long long rowoff = (static_cast<long long>(b) * p.L + t) * TC_C;
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int col = half * 128 + cc * 32;
+                    const int col = half * 128 + cc * 32;     // skip channel of r[0]
                     uint32_t r[32];
                     tmem_ld_32x32(t_lane + 256 + col, r);
                     tmem_ld_wait();
-                    if (valid) {
-                        float4* sk = reinterpret_cast<float4*>(p.skip + rowoff + col);
+                    uint8_t* brow = stg + (cc & 1) * 4096 + lane * 128;
+                    // box (cc & 1) was handed to TMA two commits ago (by the residual half or by chunk cc - 2)
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
 #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            float4 v;
-                            v.x = __uint_as_float(r[4 * m + 0]) + s_b2[256 + col + 4 * m + 0];
-                            v.y = __uint_as_float(r[4 * m + 1]) + s_b2[256 + col + 4 * m + 1];
-                            v.z = __uint_as_float(r[4 * m + 2]) + s_b2[256 + col + 4 * m + 2];
-                            v.w = __uint_as_float(r[4 * m + 3]) + s_b2[256 + col + 4 * m + 3];
-                            if (!p.first_layer) {
-                                const float4 o = sk[m];
-                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                            }
-                            sk[m] = v;
-                        }
+                    for (int m = 0; m < 8; ++m) {
+                        float4 v;
+                        v.x = __uint_as_float(r[4 * m + 0]) + s_b2[256 + col + 4 * m + 0];
+                        v.y = __uint_as_float(r[4 * m + 1]) + s_b2[256 + col + 4 * m + 1];
+                        v.z = __uint_as_float(r[4 * m + 2]) + s_b2[256 + col + 4 * m + 2];
+                        v.w = __uint_as_float(r[4 * m + 3]) + s_b2[256 + col + 4 * m + 3];
+                        const int chunk = m ^ (lane & 7);
+                        *reinterpret_cast<float4*>(brow + chunk * 16) = v;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !(p.dbg & 1)) {
+                        if (p.first_layer) tma_store_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
+                        else               tma_reduce_add_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
+                        tma_store_commit();
                     }
                 }
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_tempty[1]);
+                if (lane == 0) {
+                    mbar_arrive(&bar_tempty[1]);
+                    tma_store_wait_read<0>();          // z is rewritten by the next tile's epilogue 1
+                }
+                __syncwarp();
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores fully performed before exit
     }
 
     tc_fence_before_sync();

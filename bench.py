@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Benchmark of the EDM sampling hot path (BASELINE.json metric: DiffWave SC09 EDM-Heun samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: the full 18-step EDM-Heun trajectory (35
+network evaluations of DiffWave C=256 / 36 layers / L=16000) for `--batch` samples per GPU
+(default 256 = BASELINE.json configs[1]), synthetic N(0,1) noise, seeded random weights (the
+zero-initialised output layer re-randomised), bf16 tensor-core path.
+
+Prints ONE JSON line (rank 0). `value` = whole-job samples/s with inputs resident in HBM; `e2e` =
+the same metric through the public sampler API with pinned HOST buffers (H2D of the noise and D2H
+of the waveforms inside the timed region). Multi-GPU (torchrun, one process per GPU): the batch is
+sharded, every rank samples its own `--batch` waveforms with no collective on the data path
+(weak scaling); time = max over ranks.
+
+`--impl reference` times the reference algorithm on the host CPU (the oracle port in oracle/, which
+tests/test_oracle_golden.py pins bit-for-bit to the reference's own fp32 outputs) on a bounded
+sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "diffwave_sc09_edm_heun18_samples_per_sec"
+UNIT = "samples/s"
+C, LAYERS, CYCLE, L, STEPS_EDM, SIGMA_DATA = 256, 36, 12, 16000, 18, 0.2
+NFE = 2 * STEPS_EDM - 1
+# algorithmic conv FLOPs per sample per network evaluation; the last block's unused
+# residual half (2.097 G) is not computed and not counted
+FLOP_BLOCK = 2 * 512 * 768 * L + 2 * 512 * 256 * L                 # 16.777 G per residual block
+FLOP_EVAL_BLOCKS = LAYERS * FLOP_BLOCK - 2 * 256 * 256 * L          # all 36 block launches
+# fused sampler step: fp32 state, fp32 net output; mid kernel r(x,F) w(d,x') = 16 B, post kernel
+# r(x,d,F) w(x) = 16 B per state element
+STEP_BYTES_PER_ELEM = 16.0
+WORKLOAD = (f"DiffWave C={C} layers={LAYERS} cycle={CYCLE}, SC09 shape 1x{L}, EDM Heun {STEPS_EDM} steps ({NFE} network "
+            f"evaluations), sigma_data={SIGMA_DATA}, Karras(0.002,80,rho=7), s_churn=0 (BASELINE.json configs[1])")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")), "hbm_gbs": p.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16 sustained, HBM copy)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:                                          # noqa: BLE001
+                pass
+            self._stop.wait(0.25)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        busy = sorted(self.samples)[len(self.samples) // 4:] if self.samples else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_eval_time(n_evals, threads):
+    """Time `n_evals` full-size network evaluations (B = 1) of the oracle port on the host."""
+    from oracle import edm as oedm, wavenet as owav
+    from oracle.weights import make_wavenet_state_dict
+    torch.set_num_threads(threads)
+    sd = make_wavenet_state_dict(C, LAYERS, seed=0)
+    net_fn = owav.make_net_fn(sd, CYCLE)
+    x = torch.randn(1, 1, L, generator=torch.Generator().manual_seed(1))
+    times = []
+    with torch.no_grad():
+        for s in ([80.0, 1.0, 0.05] * ((n_evals + 2) // 3))[:n_evals]:
+            t0 = time.perf_counter()
+            oedm.denoise(x * s, net_fn, SIGMA_DATA, sigma=s)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    evals_per_step = 2
+    for _ in range(args.warmup):
+        cpu_reference_eval_time(1, threads)
+    t = cpu_reference_eval_time(evals_per_step * max(args.steps, 1), threads)
+    t_eval = sum(t) / len(t)
+    value = 1.0 / (NFE * t_eval)                       # samples/s: one sample needs NFE evaluations
+    sample = (f"B=1 x {len(t)} full-size network evaluations (of the {NFE} one sample needs), fp32, "
+              f"extrapolated x{NFE}; torch {torch.__version__} CPU, {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * evals_per_step * t_eval, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                       "parallelism": "host CPU threads", "arm": "reference algorithm on the host CPU (oracle port, pinned "
+                       "bit-exact to the reference's fp32 outputs); bounded sample, see cpu_baseline.sample"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from audiodiffuser_b200 import EluDiffusion, EDMSampler, KarrasSchedule, WaveNetNoise, _native
+    from audiodiffuser_b200.sharding import shard_noise
+    from oracle.weights import make_wavenet_state_dict
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    net = WaveNetNoise(C, LAYERS, CYCLE, precision=args.precision)
+    net.load_state_dict(make_wavenet_state_dict(C, LAYERS, seed=0), strict=True)
+    net = net.to(dev)
+    diff = EluDiffusion(sigma_data=SIGMA_DATA)
+    sampler = EDMSampler(s_tmin=0, s_tmax=float("inf"), s_churn=0.0, s_noise=1.0, num_steps=STEPS_EDM, cond_scale=1.0,
+                         use_heun=True)
+    sigmas = KarrasSchedule(0.002, 80.0, 7.0, STEPS_EDM)().to(dev)
+    # this rank's shard of the global batch: sample g uses seed base + g, so results do not depend on world size
+    noise_host = shard_noise(global_batch=B * world, rank=rank, world=world, length=L, base_seed=1234).pin_memory()
+    noise_dev = noise_host.to(dev)
+    out_host = torch.empty_like(noise_host).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        return sampler(noise_dev, fn=diff.denoise_fn, net=net, sigmas=sigmas)
+
+    def step_e2e():
+        x = noise_host.to(dev, non_blocking=True)
+        y = sampler(x, fn=diff.denoise_fn, net=net, sigmas=sigmas)
+        out_host.copy_(y, non_blocking=True)
+        return y
+
+    for _ in range(max(args.warmup, 1)):
+        y = step_resident()
+    _native.check_async()
+    assert torch.isfinite(y).all() and float(y.abs().max()) > 0
+
+    def timed(fn, steps, timing):
+        net.set_timing(timing)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    ms_res = timed(step_resident, args.steps, True)
+    tm = net.timers()                                    # per-kernel-class CUDA-event time, this rank, timed region
+    ms_e2e = timed(step_e2e, args.steps, False)
+    clk = clocks.stop() if clocks else None
+    _native.check_async()
+
+    if rank == 0:
+        peaks = load_peaks()
+        total = B * world * args.steps
+        value = total / (ms_res * 1e-3)
+        e2e = total / (ms_e2e * 1e-3)
+        conv_ms, conv_n = tm["conv"]
+        step_ms, step_n = tm["step"]
+        launches = sum(v[1] for v in tm.values())
+        conv_tflops = (B * FLOP_EVAL_BLOCKS * NFE * args.steps) / (conv_ms * 1e-3) / 1e12 if conv_ms else None
+        step_bytes = STEP_BYTES_PER_ELEM * B * L
+        n_step_main = (2 * STEPS_EDM - 1) * args.steps   # mid + post (+ final Euler) kernels
+        step_gbs = (step_bytes * n_step_main) / (step_ms * 1e-3) / 1e9 if step_ms else None
+        roofline = {"bound": "tensor", "kernel": "wavenet_block_tc_kernel", "achieved": conv_tflops,
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": conv_tflops / peaks["bf16_tflops"] if conv_tflops else None,
+                    "traffic": None, "peak_source": peaks["source"],
+                    "launches": conv_n, "avg_launch_ms": conv_ms / conv_n if conv_n else None,
+                    "flop_per_launch": B * FLOP_EVAL_BLOCKS / LAYERS}
+        step_roofline = {"bound": "hbm", "kernel": "edm_kernel<OP_MID|OP_POST>", "achieved": step_gbs,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": step_gbs / peaks["hbm_gbs"] if step_gbs else None,
+                         "bytes_per_launch": step_bytes, "launches": step_n,
+                         "note": "state of B*L fp32 elements (16 MB at B=256) is L2-resident; launch-latency bound"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 1), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD,
+                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
+                           "l2": "working set per launch (h 2x2.1 GB + skip 4.2 GB at B=256) >> 126 MB L2: no flush needed"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": noise_host.numel() * 4,
+                        "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "roofline_step_kernel": step_roofline,
+                "kernel_ms": {k: v[0] for k, v in tm.items()},
+                "clocks": clk}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            t = cpu_reference_eval_time(4, threads)
+            t_eval = sum(t[1:]) / len(t[1:])
+            line["cpu_baseline"] = {"value": 1.0 / (NFE * t_eval), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"B=1 x 3 full-size network evaluations after 1 warm-up (of {NFE} per sample), "
+                                              f"fp32 torch-CPU oracle port, extrapolated x{NFE}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

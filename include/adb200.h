@@ -125,12 +125,14 @@ int adb_wavenet_sample_edm(adb_wavenet* net, const float* noise_dev, const float
                            int precision, void* workspace_dev, int64_t workspace_bytes, int* nfe_out, void* stream);
 
 /* Per-kernel-class device time of the last *_timed call below (microseconds, CUDA events). */
-#define ADB_TIMER_CONV 0   /* residual-block kernels (+ tail GEMM) */
+#define ADB_TIMER_CONV 0   /* residual-block kernels (the dominant kernel) */
 #define ADB_TIMER_STEP 1   /* fused sampler-step kernels */
 #define ADB_TIMER_AUX 2    /* embedding MLP / E table / input projection */
-#define ADB_TIMER_COUNT 3
+#define ADB_TIMER_TAIL 3   /* skip-projection + output-projection kernel(s) */
+#define ADB_TIMER_COUNT 4
 /* Enable (1) / disable (0) event timing around kernel classes inside adb_wavenet_sample_edm and
- * adb_wavenet_forward; adb_wavenet_timers() synchronises and returns accumulated ms and launch counts. */
+ * adb_wavenet_forward; adb_wavenet_timers() synchronises and returns accumulated ms and kernel-launch counts per class
+ * (launch counts are maintained whether or not timing is enabled). */
 int adb_wavenet_set_timing(adb_wavenet* net, int enabled);
 int adb_wavenet_timers(adb_wavenet* net, double* ms_out /*[ADB_TIMER_COUNT]*/, int64_t* launches_out /*[ADB_TIMER_COUNT]*/);
 

@@ -155,6 +155,18 @@ def main():
             outs[f"net_sigma_{s_}"] = net((noise[:, 0] * s_) * float((s_ ** 2 + 0.04) ** -0.5),
                                           torch.full((B,), 0.25 * float(np.log(s_))))
             outs[f"den_sigma_{s_}"] = diff.denoise_fn(noise * s_, net=adapter, sigma=torch.tensor(s_), inference=True)
+        # The same algorithm evaluated in fp64 (the reference modules themselves cannot run in double:
+        # diffusion_embedding, wavenet.py:88-92, builds an fp32 table). The oracle restatement, which
+        # reproduces the reference's fp32 outputs bit-for-bit (asserted here), is run in fp64 instead.
+        # It shows how far the reference's own fp32 output is from exact arithmetic (1.0e-5 relative at
+        # sigma = 80), which bounds what any fp32-vs-fp32 comparison can show.
+        from oracle import edm as oedm, wavenet as owav
+        sd32 = make_wavenet_state_dict(C, layers, seed)
+        sd64 = {k: v.double() for k, v in sd32.items()}
+        for s_ in [80.0, 1.0, 0.002]:
+            o32 = oedm.denoise(noise * s_, owav.make_net_fn(sd32, cycle), 0.2, sigma=s_)
+            assert torch.equal(o32, outs[f"den_sigma_{s_}"]), "oracle no longer bit-identical to the reference"
+            outs[f"den64_sigma_{s_}"] = oedm.denoise(noise.double() * s_, owav.make_net_fn(sd64, cycle), 0.2, sigma=s_)
         sampler = ref.sampler_edm.EDMSampler(s_tmin=0, s_tmax=float("inf"), s_churn=0.0, s_noise=1.0,
                                              num_steps=18, cond_scale=1.0, use_heun=True)
         outs["heun18"] = sampler(noise, fn=diff.denoise_fn, net=adapter, sigmas=sig18)

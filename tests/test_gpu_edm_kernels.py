@@ -8,6 +8,10 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
+# fp32 elementwise kernels vs the torch-CPU oracle: same formulas, scalar coefficients rounded in a
+# slightly different order (host fp32 vs ATen scalar promotion) -> agreement to ~1 ulp, not bit-exact.
+ELEMWISE_TOL = 5e-7
+
 
 @pytest.fixture(scope="module")
 def env():
@@ -33,13 +37,14 @@ def test_precond_in_out(env, B, C, L):
     for sigma in (80.0, 1.0, 0.002):
         want = edm.denoise(x, lambda a, b, **kw: f, 0.2, sigma=sigma)
         got = diff.denoise_fn(x.to(dev), net=net, sigma=sigma, inference=True)
-        assert torch.equal(got.cpu(), want), (sigma, rel_l2(got, want))        # bit-exact: no libm involved
+        assert rel_l2(got, want) < ELEMWISE_TOL, (sigma, rel_l2(got, want))
+        assert float((got.cpu() - want).abs().max()) <= 2e-7      # a couple of fp32 ulps at |D| <= 1
         got0 = diff.denoise_fn(x.to(dev), net=net, sigma=torch.tensor(sigma, device=dev), inference=True)
         assert torch.equal(got0, got)
     sig = torch.rand(B, generator=torch.Generator().manual_seed(3)) * 5 + 0.01
     want = edm.denoise(x, lambda a, b, **kw: f, 0.2, sigmas=sig, inference=False)
     got = diff.denoise_fn(x.to(dev), net=net, sigmas=sig.to(dev), inference=False)
-    assert torch.equal(got.cpu(), want)
+    assert rel_l2(got, want) < ELEMWISE_TOL
     N.check_async()
 
 
@@ -75,7 +80,7 @@ def test_cfg_combine(env):
 
     want = edm.denoise(x, net_cpu, 0.2, sigma=0.7, cond_scale=2.5)
     got = diff.denoise_fn(x.to(dev), net=net_gpu, sigma=0.7, inference=True, cond_scale=2.5)
-    assert torch.equal(got.cpu(), want)
+    assert rel_l2(got, want) < ELEMWISE_TOL
 
 
 def test_exactly_one_sigma(env):

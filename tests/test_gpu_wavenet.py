@@ -146,8 +146,17 @@ def test_full_size_vs_reference_golden(dev, precision):
     noise = torch.from_numpy(g["noise"]).to(dev)
     for s in (80.0, 1.0, 0.002):
         out = diff.denoise_fn(noise * s, net=net, sigma=s, inference=True)
-        e = rel_l2(out, g[f"den_sigma_{s}"])
-        assert e < TOL[precision], (precision, s, e)
+        e32 = rel_l2(out, g[f"den_sigma_{s}"])           # vs the reference's own fp32 output
+        e64 = rel_l2(out, g[f"den64_sigma_{s}"])         # vs the same algorithm evaluated in fp64
+        print(f"full-size {precision} sigma={s}: rel-L2 vs ref fp32 {e32:.3e}, vs fp64 {e64:.3e}")
+        if precision == "fp32":
+            # The reference's fp32 output is itself 1.03e-5 (sigma=80) / 8.3e-6 (sigma=1) away from the fp64
+            # evaluation after 36 layers, so two independent fp32 implementations can differ by up to the sum
+            # of their errors: hold 1e-5 against the fp64 evaluation and 2e-5 against the reference's fp32.
+            assert e64 < 1e-5, (s, e64)
+            assert e32 < 2e-5, (s, e32)
+        else:
+            assert e32 < TOL["bf16"], (s, e32)
     smp = EDMSampler(s_churn=0.0, s_noise=1.0, num_steps=steps)
     x = smp(noise, fn=diff.denoise_fn, net=net, sigmas=torch.from_numpy(g["sigmas"]).to(dev))
     N.check_async()
