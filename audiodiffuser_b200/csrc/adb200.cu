@@ -60,6 +60,17 @@ extern "C" int adb_device_check(int device) {
     return ADB_OK;
 }
 
+// debug: in-kernel cycle counters of the residual-block kernel (see wavenet_tc.cuh); not part of the product ABI
+extern "C" int adb_debug_tc_cycles(unsigned long long* out16, int reset) {
+    CK(cudaDeviceSynchronize());
+    if (out16) CK(cudaMemcpyFromSymbol(out16, g_tc_cycles, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {};
+        CK(cudaMemcpyToSymbol(g_tc_cycles, z, sizeof z));
+    }
+    return ADB_OK;
+}
+
 extern "C" int adb_check_async(void) {
     CK(cudaDeviceSynchronize());
     SpinGuardState st;
@@ -235,7 +246,8 @@ struct adb_wavenet {
     __nv_bfloat16* wsp_tc = nullptr;  // [4][256][64]
     float* mtab = nullptr;            // [512][layers*3*512]  (W1[tap] Wp)^T
     float* cvec = nullptr;            // [layers*3*512]       W1[tap] bp (+ b1 for the centre tap)
-    CUtensorMap tm_w, tm_wsp;
+    CUtensorMap tm_w, tm_w2, tm_w4, tm_wsp;     // weight maps with box rows 256 / 128 / 64 (cluster 1 / 2 / 4)
+    int cluster = 2;                            // CTAs per cluster for the residual-block kernel (ADB_TC_CLUSTER)
     std::vector<HMap> hmaps;
     bool tc_ready = false;
     // timing
@@ -310,12 +322,12 @@ static cudaError_t dmalloc(adb_wavenet* n, T** p, size_t count) {
     return e;
 }
 
-static int make_weight_map(CUtensorMap* map, const void* base, uint64_t rows) {
+static int make_weight_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows = 256) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {64, rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, 256};
+    cuuint32_t box[2] = {64, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -501,7 +513,14 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(cudaDeviceSynchronize());
         cudaFree(wpT);
         int rc2 = make_weight_map(&n->tm_w, n->wtc, static_cast<uint64_t>(layers) * 32 * 256);
+        if (!rc2) rc2 = make_weight_map(&n->tm_w2, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 128);
+        if (!rc2) rc2 = make_weight_map(&n->tm_w4, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 64);
         if (!rc2) rc2 = make_weight_map(&n->tm_wsp, n->wsp_tc, 4 * 256);
+        {
+            const char* e = getenv("ADB_TC_CLUSTER");
+            if (e) n->cluster = atoi(e);
+            if (n->cluster != 1 && n->cluster != 2 && n->cluster != 4) n->cluster = 2;
+        }
         if (rc2) { adb_wavenet_destroy(n); cudaFree(d_jobs); cudaFree(d_scale); return rc2; }
         CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
@@ -687,6 +706,21 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     const int tiles_per_b = (L + TC_TILE_T - 1) / TC_TILE_T;
     const int num_tiles = tiles_per_b * B;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    // residual-block kernel: persistent clusters of `cl` CTAs (weights multicast inside a cluster)
+    const int cl = n->cluster;
+    int max_clusters = num_sms / cl;
+    if (cl > 1) {
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(num_sms / cl * cl); qc.blockDim = dim3(TC_THREADS); qc.dynamicSmemBytes = TC_BLOCK_SMEM_BYTES;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = cl; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa; qc.numAttrs = 1;
+        int mc = 0;
+        if (cudaOccupancyMaxActiveClusters(&mc, wavenet_block_tc_kernel, &qc) == cudaSuccess && mc > 0) max_clusters = mc;
+    }
+    const int groups = (num_tiles + cl - 1) / cl;
+    const int grid_block = (groups < max_clusters ? groups : max_clusters) * cl;
     __nv_bfloat16 *hin = w.hbA, *hout = w.hbB;
     for (int l = 0; l < layers; ++l) {
         ScopedTimer t(n, ADB_TIMER_CONV, st);
@@ -701,8 +735,17 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
         bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
         bp.first_layer = (l == 0); bp.write_h = (l + 1 < layers) || (l < dump_layers);
         { const char* e = getenv("ADB_DEBUG_FLAGS"); bp.dbg = e ? atoi(e) : 0; }
-        wavenet_block_tc_kernel<<<grid, TC_THREADS, TC_BLOCK_SMEM_BYTES, st>>>(m_h, n->tm_w, m_hout, m_skip, bp);
-        CK(cudaGetLastError());
+        bp.cluster = cl;
+        {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(grid_block); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = TC_BLOCK_SMEM_BYTES; lc.stream = st;
+            cudaLaunchAttribute la[1];
+            la[0].id = cudaLaunchAttributeClusterDimension;
+            la[0].val.clusterDim.x = cl; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+            lc.attrs = la; lc.numAttrs = 1;
+            const CUtensorMap& m_w = cl == 1 ? n->tm_w : (cl == 2 ? n->tm_w2 : n->tm_w4);
+            CK(cudaLaunchKernelEx(&lc, wavenet_block_tc_kernel, m_h, m_w, m_hout, m_skip, bp));
+        }
         if (l < dump_layers) {
             cvt_bf16_f32_kernel<<<grid_for(BL * C), 256, 0, st>>>(hout, dump_h + l * BL * C, BL * C);
             CK(cudaMemcpyAsync(dump_skip + l * BL * C, w.skip, sizeof(float) * BL * C, cudaMemcpyDeviceToDevice, st));

@@ -32,6 +32,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 
 namespace adb {
@@ -54,12 +55,13 @@ struct BlockTcSmem {
     static constexpr int evec = z + TC_Z_BYTES;                 // 3 x 512 fp32
     static constexpr int b2 = evec + 3 * 512 * 4;               // 512 fp32
     static constexpr int ident = b2 + 512 * 4;                  // [64 n][64 k] bf16 identity, K-major SW128 (8 KB)
-    static constexpr int bars = ident + 64 * 128;               // mbarriers
+    static constexpr int esum = ident + 64 * 128;               // 512 fp32: E0 + E1 + E2 (gate half pre-scaled by 0.5)
+    static constexpr int bars = esum + 512 * 4;                 // mbarriers
     static constexpr int tmem_ptr = bars + 16 * 8;
     static constexpr int total = tmem_ptr + 16;
 };
 static_assert(BlockTcSmem::ident % 1024 == 0, "identity tile must sit on a swizzle-atom boundary");
-constexpr int TC_BLOCK_SMEM_BYTES = BlockTcSmem::total + 1024;  // + alignment slack
+constexpr int TC_BLOCK_SMEM_BYTES = BlockTcSmem::total;
 
 struct BlockTcParams {
     const float* E;                 // [B][layers][3][512] epilogue-1 constants for this evaluation
@@ -72,7 +74,17 @@ struct BlockTcParams {
     int first_layer;                // 1: skip = value, 0: skip += value
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
     int dbg;                        // debug bits (ADB_DEBUG_FLAGS): 1 = skip epilogue-2 global memory traffic
+    int cluster;                    // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across the cluster
 };
+
+// Optional in-kernel cycle accounting (BlockTcParams::dbg & 2): where each role waits.
+//  0 mma: wait accumulator-drained (G1 jobs)   1 mma: wait accumulator-drained (G2 jobs)   2 mma: wait z ready
+//  3 mma: wait TMA stage full                   4 mma: total                                 5 producer: wait stage empty
+//  6 producer: total                            7 epi(warp 2): wait accumulator full (G1)    8 epi: epilogue-1 work
+//  9 epi: wait accumulator full (G2)           10 epi: epilogue-2 work                       11 epi: total
+__device__ unsigned long long g_tc_cycles[16];
+#define TC_DBG_T0(var) long long var = 0; if (p.dbg & 2) var = clock64()
+#define TC_DBG_ACC(idx, var) if (p.dbg & 2) dbg_acc[idx] += clock64() - var
 
 enum TcWaitSite : uint32_t {
     SITE_PROD_EMPTY = 1, SITE_MMA_TEMPTY = 2, SITE_MMA_ZREADY = 3, SITE_MMA_FULL = 4, SITE_EPI_TFULL = 5,
@@ -87,10 +99,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_hout, const __grid_constant__ CUtensorMap tm_skip,
                         const BlockTcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
     float* s_evec = reinterpret_cast<float*>(smem + BlockTcSmem::evec);
     float* s_b2 = reinterpret_cast<float*>(smem + BlockTcSmem::b2);
+    float* s_esum = reinterpret_cast<float*>(smem + BlockTcSmem::esum);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BlockTcSmem::bars);
     uint64_t* bar_full = bars;                   // [TC_STAGES]  TMA -> MMA
     uint64_t* bar_empty = bars + TC_STAGES;      // [TC_STAGES]  MMA -> TMA
@@ -110,7 +122,7 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+            for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], p.cluster); }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&bar_tfull[i], 1);
                 mbar_init(&bar_tempty[i], TC_EPI_THREADS / 32);
@@ -140,22 +152,38 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();      // every CTA's barriers exist before any remote arrive / multicast write
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
     constexpr uint32_t IDESC = umma_idesc_bf16_f32(128, 256);
     constexpr uint32_t IDESC_N64 = umma_idesc_bf16_f32(128, 64);
+    constexpr uint32_t IDESC_F16 = umma_idesc_f16_f32(128, 256);     // GEMM2: z and W2 are fp16
+    // Tile schedule: clusters walk groups of `cluster` consecutive tiles; every CTA of a cluster runs the same
+    // number of iterations (a CTA whose tile is past the end still moves its share of the weights and
+    // consumes its stages, but stores nothing).
+    const int crank = p.cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int cluster_id = blockIdx.x / p.cluster;
+    const int num_clusters = gridDim.x / p.cluster;
+    const int num_groups = (p.num_tiles + p.cluster - 1) / p.cluster;
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cluster) - 1u);
+    const int w_rows = 256 / p.cluster;           // rows of each weight tile this CTA fetches for the cluster
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         uint32_t stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int b = tile / p.tiles_per_b;
+        long long dbg_acc[16] = {};
+        TC_DBG_T0(tp_all);
+        for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+            const int tile = grp * p.cluster + crank;
+            const int b = tile / p.tiles_per_b;           // >= B for a padding tile: TMA zero-fills
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
             for (int job = 0; job < 4; ++job) {
                 if (job == 2 && !p.write_h) continue;
                 const int nkb = job < 2 ? 12 : 4;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    TC_DBG_T0(tw);
                     mbar_wait(&bar_empty[stage], phase ^ 1, SITE_PROD_EMPTY, stage);
+                    TC_DBG_ACC(5, tw);
                     if (lane == 0) {
                         uint8_t* sa = smem + BlockTcSmem::stages + stage * TC_STAGE_BYTES;
                         uint8_t* sb = sa + TC_A_BYTES;
@@ -172,34 +200,53 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                         } else {
                             mbar_arrive_expect_tx(&bar_full[stage], TC_B_BYTES);
                         }
-                        tma_load_2d(sb, &tm_w, &bar_full[stage], 0, wblk * 256);
+                        if (p.cluster == 1) tma_load_2d(sb, &tm_w, &bar_full[stage], 0, wblk * 256);
+                        else tma_load_2d_mc(sb + crank * w_rows * 128, &tm_w, &bar_full[stage], 0, wblk * 256 + crank * w_rows,
+                                            mc_mask);
                     }
                     __syncwarp();
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        TC_DBG_ACC(6, tp_all);
+        if ((p.dbg & 2) && lane == 0) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         uint32_t stage = 0, phase = 0;
         uint32_t use0 = 0, use1 = 0;        // jobs issued so far into accumulator 0 / 1
         uint32_t it = 0;
         const uint32_t z_addr = smem_u32(smem + BlockTcSmem::z);
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        long long dbg_acc[16] = {};
+        TC_DBG_T0(tm_all);
+        for (int grp = cluster_id; grp < num_groups; grp += num_clusters, ++it) {
             for (int job = 0; job < 4; ++job) {
                 if (job == 2 && !p.write_h) continue;
                 const int buf = job & 1;
                 const uint32_t use = buf ? use1 : use0;
+                TC_DBG_T0(tw0);
                 mbar_wait(&bar_tempty[buf], (use & 1) ^ 1, SITE_MMA_TEMPTY, job);
-                if (job == 2 || (job == 3 && !p.write_h)) {
+                TC_DBG_ACC(job < 2 ? 0 : 1, tw0);
+                const bool first_g2 = (job == 2 || (job == 3 && !p.write_h));
+                if (first_g2) {
+                    // z K-blocks 0,1 come from epilogue 1a, K-blocks 2,3 from epilogue 1b: start on the first
+                    // half while 1b is still running (the second wait sits inside the K loop)
+                    TC_DBG_T0(tw1);
                     mbar_wait(&bar_zready[0], it & 1, SITE_MMA_ZREADY, 0);
-                    mbar_wait(&bar_zready[1], it & 1, SITE_MMA_ZREADY, 1);
+                    TC_DBG_ACC(2, tw1);
                 }
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + buf * 256;
                 const int nkb = job < 2 ? 12 : 4;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    if (first_g2 && kb == 2) {
+                        TC_DBG_T0(tw1);
+                        mbar_wait(&bar_zready[1], it & 1, SITE_MMA_ZREADY, 1);
+                        TC_DBG_ACC(2, tw1);
+                    }
+                    TC_DBG_T0(tw2);
                     mbar_wait(&bar_full[stage], phase, SITE_MMA_FULL, stage);
+                    TC_DBG_ACC(3, tw2);
                     tc_fence_after_sync();
                     if (lane == 0) {
                         const uint32_t sa = smem_u32(smem + BlockTcSmem::stages + stage * TC_STAGE_BYTES);
@@ -208,7 +255,8 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             umma_bf16_ss(d_tmem, umma_desc_sw128_kmajor(a_addr + k * 32),
-                                         umma_desc_sw128_kmajor(b_addr + k * 32), IDESC, (kb | k) != 0 ? 1u : 0u);
+                                         umma_desc_sw128_kmajor(b_addr + k * 32), job < 2 ? IDESC : IDESC_F16,
+                                         (kb | k) != 0 ? 1u : 0u);
                         }
                         if (job == 2) {
                             // + h: D[:, 64 kb .. 64 kb + 63] += h_tile * I   (exact: bf16 x 1.0 in fp32)
@@ -218,7 +266,8 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                                 umma_bf16_ss(d_tmem + kb * 64, umma_desc_sw128_kmajor(sa + k * 32),
                                              umma_desc_sw128_kmajor(id_addr + k * 32), IDESC_N64, 1u);
                         }
-                        umma_commit(&bar_empty[stage]);
+                        if (p.cluster == 1) umma_commit(&bar_empty[stage]);
+                        else umma_commit_mc(&bar_empty[stage], mc_mask);      // frees this stage in every CTA of the cluster
                         if (kb == nkb - 1) umma_commit(&bar_tfull[buf]);
                     }
                     __syncwarp();
@@ -227,6 +276,9 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 if (buf) ++use1; else ++use0;
             }
         }
+        TC_DBG_ACC(4, tm_all);
+        if ((p.dbg & 2) && lane == 0)
+            for (int i = 0; i < 5; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
     } else {
         // ===================== epilogue warps =====================
         const int ew = warp - 2;              // 0..7
@@ -236,26 +288,38 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         uint8_t* zbase = smem + BlockTcSmem::z;
         uint32_t use0 = 0, use1 = 0;
+        long long dbg_acc[16] = {};
+        TC_DBG_T0(te_all);
         const float* Ec = s_evec + 512;       // tap 1 (centre, + conv bias)
         const float* E0 = s_evec;             // tap 0 (t - d)
         const float* E2 = s_evec + 1024;      // tap 2 (t + d)
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+            const int tile = grp * p.cluster + crank;
+            const bool tile_valid = tile < p.num_tiles;
             const int b = tile / p.tiles_per_b;
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
             const int t = t0 + row;
             named_bar_sync(1, TC_EPI_THREADS);
             {
-                const float* src = p.E + (static_cast<long long>(b) * p.layers + p.layer) * 1536;
+                const float* src = p.E + (static_cast<long long>(tile_valid ? b : 0) * p.layers + p.layer) * 1536;
                 for (int i = threadIdx.x - 64; i < 1536; i += TC_EPI_THREADS) s_evec[i] = src[i];
             }
             named_bar_sync(1, TC_EPI_THREADS);
+            for (int i = threadIdx.x - 64; i < 512; i += TC_EPI_THREADS)
+                s_esum[i] = (s_evec[i] + s_evec[512 + i] + s_evec[1024 + i]) * (i < 256 ? 0.5f : 1.0f);
+            named_bar_sync(1, TC_EPI_THREADS);
             const float m_lo = (t >= p.dil) ? 1.0f : 0.0f;
             const float m_hi = (t < p.L - p.dil) ? 1.0f : 0.0f;
+            // interior tile: every row sees all three taps, so the step-embedding term is one vector
+            const bool interior = (t0 >= p.dil) && (t0 + TC_TILE_T - 1 < p.L - p.dil);
 
             // ---- epilogue 1: gate, two jobs (channels 128 j .. 128 j + 127) ----
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
+                TC_DBG_T0(tw);
                 mbar_wait(&bar_tfull[j], (j ? use1 : use0) & 1, SITE_EPI_TFULL, j);
+                TC_DBG_ACC(7, tw);
+                TC_DBG_T0(tk);
                 if (j) ++use1; else ++use0;
                 tc_fence_after_sync();
 #pragma unroll 1
@@ -266,23 +330,38 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                     tmem_ld_32x32(t_lane + j * 256 + 128 + col, f);
                     tmem_ld_wait();
                     const int c0 = 128 * j + col;                 // original channel of g[0]
+                    // z = sigmoid(g) * tanh(f) with sigmoid(g) = 0.5 tanh(g / 2) + 0.5, evaluated two channels at a
+                    // time in fp16x2 (one MUFU per tanh pair); z in (-1, 1) is stored as fp16 for GEMM2
                     uint32_t packed[16];
+                    if (interior) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        float zv[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int c = c0 + i + u;
-                            float gv = __uint_as_float(g[i + u]) + Ec[c];
-                            float fv = __uint_as_float(f[i + u]) + Ec[256 + c];
-                            gv = fmaf(m_lo, E0[c], gv);
-                            fv = fmaf(m_lo, E0[256 + c], fv);
-                            gv = fmaf(m_hi, E2[c], gv);
-                            fv = fmaf(m_hi, E2[256 + c], fv);
-                            const float sg = fmaf(0.5f, tanh_fast(0.5f * gv), 0.5f);
-                            zv[u] = sg * tanh_fast(fv);
+                        for (int i = 0; i < 32; i += 2) {
+                            const float g0 = fmaf(__uint_as_float(g[i]), 0.5f, s_esum[c0 + i]);
+                            const float g1 = fmaf(__uint_as_float(g[i + 1]), 0.5f, s_esum[c0 + i + 1]);
+                            const float f0 = __uint_as_float(f[i]) + s_esum[256 + c0 + i];
+                            const float f1 = __uint_as_float(f[i + 1]) + s_esum[256 + c0 + i + 1];
+                            const uint32_t tg = tanh_f16x2(pack_f16x2(g0, g1));
+                            const uint32_t tf = tanh_f16x2(pack_f16x2(f0, f1));
+                            packed[i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
                         }
-                        packed[i >> 1] = pack_bf16x2(zv[0], zv[1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float gv[2], fv[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int c = c0 + i + u;
+                                gv[u] = __uint_as_float(g[i + u]) + Ec[c];
+                                fv[u] = __uint_as_float(f[i + u]) + Ec[256 + c];
+                                gv[u] = fmaf(m_lo, E0[c], gv[u]);
+                                fv[u] = fmaf(m_lo, E0[256 + c], fv[u]);
+                                gv[u] = 0.5f * fmaf(m_hi, E2[c], gv[u]);
+                                fv[u] = fmaf(m_hi, E2[256 + c], fv[u]);
+                            }
+                            const uint32_t tg = tanh_f16x2(pack_f16x2(gv[0], gv[1]));
+                            const uint32_t tf = tanh_f16x2(pack_f16x2(fv[0], fv[1]));
+                            packed[i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
+                        }
                     }
                     // z K-block (64 channels) = 2 j + half ; 16-byte chunk inside the 128-byte row = 4 cc + m
                     uint8_t* zrow = zbase + (2 * j + half) * TC_A_BYTES + row * 128;
@@ -300,19 +379,21 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                     mbar_arrive(&bar_tempty[j]);
                     mbar_arrive(&bar_zready[j]);
                 }
+                TC_DBG_ACC(8, tk);
             }
 
-            // ---- epilogue 2: both GEMM2 halves, after the skip half (the last MMAs reading z) has finished.
-            //      Each warp owns 8 KB of the idle z buffer as two 4 KB transposition boxes (32 rows x 128 B,
-            //      128-byte swizzle) that leave through TMA.
-            mbar_wait(&bar_tfull[1], use1 & 1, SITE_EPI_TFULL, 3);
-            ++use1;
-            uint8_t* stg = zbase + ew * 8192;
-            const int trow = t0 + q * 32;                 // first time step of this warp's 32 rows
+            // ---- epilogue 2r: residual half -> h_out, stored straight from registers as soon as the residual
+            //      GEMM is done (the skip GEMM is still reading z, so no staging buffer is free yet). Each thread
+            //      owns one time row and writes 64 contiguous bytes per chunk.
+            const long long rowoff = (static_cast<long long>(b) * p.L + t) * TC_C;
             if (p.write_h) {
+                TC_DBG_T0(tw3);
                 mbar_wait(&bar_tfull[0], use0 & 1, SITE_EPI_TFULL, 2);
+                TC_DBG_ACC(9, tw3);
+                TC_DBG_T0(tk3);
                 ++use0;
                 tc_fence_after_sync();
+                const bool st_ok = tile_valid && (t < p.L) && !(p.dbg & 1);
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     const int col = half * 128 + cc * 32;     // residual channel of r[0]
@@ -326,26 +407,28 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                         const float v1 = (__uint_as_float(r[i + 1]) + s_b2[col + i + 1]) * 0.70710678118654752f;
                         pk[i >> 1] = pack_bf16x2(v0, v1);
                     }
-                    // box (cc >> 1) holds 64 channels; this chunk is its 16-byte chunks 4 (cc & 1) .. + 3
-                    uint8_t* brow = stg + (cc >> 1) * 4096 + lane * 128;
+                    if (st_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.h_out + rowoff + col);
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const int chunk = (4 * (cc & 1) + m) ^ (lane & 7);
-                        *reinterpret_cast<uint4*>(brow + chunk * 16) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
-                    }
-                    if (cc & 1) {
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0 && !(p.dbg & 1)) {
-                            tma_store_3d(&tm_hout, stg + (cc >> 1) * 4096, half * 128 + (cc >> 1) * 64, trow, b);
-                            tma_store_commit();
-                        }
+                        for (int m = 0; m < 4; ++m) dst[m] = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
                     }
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[0]);
+                TC_DBG_ACC(10, tk3);
             }
+
+            // ---- epilogue 2s: skip half, after the last MMAs reading z have finished. Each warp owns 8 KB of
+            //      the now idle z buffer as two 4 KB transposition boxes (32 rows x 128 B, 128-byte swizzle) that
+            //      leave through TMA reduce-add.
+            TC_DBG_T0(tw2);
+            mbar_wait(&bar_tfull[1], use1 & 1, SITE_EPI_TFULL, 3);
+            TC_DBG_ACC(9, tw2);
+            TC_DBG_T0(tk2);
+            ++use1;
+            uint8_t* stg = zbase + ew * 8192;
+            const int trow = t0 + q * 32;                 // first time step of this warp's 32 rows
             {
                 tc_fence_after_sync();
 #pragma unroll 1
@@ -370,7 +453,7 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && !(p.dbg & 1)) {
+                    if (lane == 0 && tile_valid && !(p.dbg & 1)) {
                         if (p.first_layer) tma_store_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
                         else               tma_reduce_add_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
                         tma_store_commit();
@@ -384,12 +467,17 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 }
                 __syncwarp();
             }
+            TC_DBG_ACC(10, tk2);
         }
+        TC_DBG_ACC(11, te_all);
+        if ((p.dbg & 2) && warp == 2 && lane == 0)
+            for (int i = 7; i < 12; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores fully performed before exit
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();      // no CTA leaves while a peer may still signal its barriers
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512);
@@ -413,7 +501,7 @@ struct TailTcSmem {
     static constexpr int tmem_ptr = bars + 32;
     static constexpr int total = tmem_ptr + 16;
 };
-constexpr int TC_TAIL_SMEM_BYTES = TailTcSmem::total + 1024;
+constexpr int TC_TAIL_SMEM_BYTES = TailTcSmem::total;
 
 struct TailTcParams {
     const float* skip;      // [B][L][256]
@@ -427,8 +515,7 @@ struct TailTcParams {
 
 __global__ void __launch_bounds__(256, 1)
 wavenet_tail_tc_kernel(const __grid_constant__ CUtensorMap tm_wsp, const TailTcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     float* s_bsp = reinterpret_cast<float*>(smem + TailTcSmem::bsp);
     float* s_wout = reinterpret_cast<float*>(smem + TailTcSmem::wout);
     float* s_part = reinterpret_cast<float*>(smem + TailTcSmem::part);
@@ -548,6 +635,10 @@ __global__ void pack_tc_layer_kernel(const float* __restrict__ w1f, const float*
         } else {
             const int j = (blk - 24) >> 2, kb = (blk - 24) & 3;
             v = w2f[static_cast<long long>(kb * 64 + k) * 512 + 256 * j + n];
+            // GEMM2 runs in fp16 (z is fp16): store the bit pattern of the fp16 value in the 16-bit slot
+            const __half hv = __float2half_rn(v);
+            out[i] = *reinterpret_cast<const __nv_bfloat16*>(&hv);
+            continue;
         }
         out[i] = __float2bfloat16_rn(v);
     }

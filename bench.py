@@ -64,13 +64,13 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
@@ -81,10 +81,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:                                          # noqa: BLE001
                 pass
-            self._stop.wait(0.25)
+            self._halt.wait(0.25)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         busy = sorted(self.samples)[len(self.samples) // 4:] if self.samples else []
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz,
