@@ -18,6 +18,7 @@
 #include "edm_kernels.cuh"
 #include "wavenet_f32.cuh"
 #include "wavenet_tc.cuh"
+#include "wavenet_tc2.cuh"
 
 using namespace adb;
 
@@ -248,6 +249,7 @@ struct adb_wavenet {
     float* cvec = nullptr;            // [layers*3*512]       W1[tap] bp (+ b1 for the centre tap)
     CUtensorMap tm_w, tm_w2, tm_w4, tm_wsp;     // weight maps with box rows 256 / 128 / 64 (cluster 1 / 2 / 4)
     int cluster = 2;                            // CTAs per cluster for the residual-block kernel (ADB_TC_CLUSTER)
+    int pair = 1;                               // 1: CTA-pair (cta_group::2) residual-block kernel (ADB_TC_PAIR=0: single-CTA kernel)
     std::vector<HMap> hmaps;
     bool tc_ready = false;
     // timing
@@ -520,9 +522,12 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             const char* e = getenv("ADB_TC_CLUSTER");
             if (e) n->cluster = atoi(e);
             if (n->cluster != 1 && n->cluster != 2 && n->cluster != 4) n->cluster = 2;
+            const char* pe = getenv("ADB_TC_PAIR");
+            if (pe) n->pair = atoi(pe) != 0;
         }
         if (rc2) { adb_wavenet_destroy(n); cudaFree(d_jobs); cudaFree(d_scale); return rc2; }
         CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
         n->tc_ready = true;
     }
@@ -736,7 +741,18 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
         bp.first_layer = (l == 0); bp.write_h = (l + 1 < layers) || (l < dump_layers);
         { const char* e = getenv("ADB_DEBUG_FLAGS"); bp.dbg = e ? atoi(e) : 0; }
         bp.cluster = cl;
-        {
+        if (n->pair) {
+            int pairs = (num_tiles + 1) / 2;
+            if (pairs > num_sms / 2) pairs = num_sms / 2;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = TC2_SMEM_BYTES; lc.stream = st;
+            cudaLaunchAttribute la[1];
+            la[0].id = cudaLaunchAttributeClusterDimension;
+            la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+            lc.attrs = la; lc.numAttrs = 1;
+            bp.cluster = 2;
+            CK(cudaLaunchKernelEx(&lc, wavenet_block_pair_kernel, m_h, n->tm_w2, m_skip, bp));
+        } else {
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3(grid_block); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = TC_BLOCK_SMEM_BYTES; lc.stream = st;
             cudaLaunchAttribute la[1];

@@ -176,3 +176,20 @@ def test_batch_rows_independent(dev):
     full = net(x, t)
     part = net(x[2:4].contiguous(), t[2:4].contiguous())
     assert torch.equal(full[2:4], part)
+
+
+@pytest.mark.parametrize("name", ["wavenet_c256_l3", "wavenet_c256_l13_dil2048", "wavenet_c256_l2_short"])
+def test_pair_kernel_vs_reference_golden(dev, name, monkeypatch):
+    """The CTA-pair (cta_group::2) residual-block kernel against the same goldens, and bit-identical to the
+    single-CTA kernel (same MMA order per accumulator element)."""
+    from audiodiffuser_b200 import _native as N
+    g = load_golden(name)
+    C, layers, cycle, B, L, seed = (int(v) for v in g["cfg"])
+    audio, t = torch.from_numpy(g["audio"]).to(dev), torch.from_numpy(g["t"]).to(dev)
+    monkeypatch.setenv("ADB_TC_PAIR", "0")
+    base = make_net(C, layers, cycle, seed, "bf16", dev)(audio, t)
+    monkeypatch.setenv("ADB_TC_PAIR", "1")
+    out = make_net(C, layers, cycle, seed, "bf16", dev)(audio, t)
+    N.check_async()
+    assert rel_l2(out, g["out"]) < TOL["bf16"], rel_l2(out, g["out"])
+    assert rel_l2(out, base) < 1e-6
