@@ -169,6 +169,26 @@ extern "C" int adb_edm_rk2(const float* x, const float* d, const float* x1, cons
     return ADB_OK;
 }
 
+extern "C" int adb_edm_heun_mid(const float* x, const float* f1, float sigma, float sigma_data, float h, float* d, float* x1,
+                                int64_t n, void* stream) {
+    REQUIRE(x && f1 && d && x1 && n > 0, "adb_edm_heun_mid: bad arguments");
+    const PrecondCoef c = precond_coef(sigma, sigma_data, sd2_of(sigma_data));
+    EdmArgs p = edm_args(x, f1, nullptr, d, x1, n, n);
+    p.s0 = sigma; p.h = h; p.c_skip0 = c.c_skip; p.c_out0 = c.c_out;
+    CK(edm_launch<OP_MID>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_heun_post(const float* x, const float* d, const float* f2, float sigma1, float sigma_data, float h,
+                                 float* x_next, int64_t n, void* stream) {
+    REQUIRE(x && d && f2 && x_next && n > 0, "adb_edm_heun_post: bad arguments");
+    const PrecondCoef c = precond_coef(sigma1, sigma_data, sd2_of(sigma_data));
+    EdmArgs p = edm_args(x, f2, nullptr, x_next, nullptr, n, n);
+    p.s1 = sigma1; p.h = h; p.hh = 0.5f * h; p.c_skip1 = c.c_skip; p.c_out1 = c.c_out;
+    CK(edm_launch<OP_POST>(p, d, S(stream)));
+    return ADB_OK;
+}
+
 extern "C" int adb_edm_noise_in(const float* x, const float* noise, const float* sigmas, float sigma_data, float* x_noisy,
                                 float* net_in, float* c_noise, int B, int64_t n_per, void* stream) {
     REQUIRE(x && noise && sigmas && x_noisy && net_in && B > 0 && n_per > 0, "adb_edm_noise_in: bad arguments");

@@ -69,6 +69,16 @@ int adb_edm_euler(const float* x_dev, const float* denoised_dev, float sigma, fl
 int adb_edm_rk2(const float* x_dev, const float* d_dev, const float* x1_dev, const float* denoised1_dev,
                 float sigma1, float h, float w0, float w1, float* out_dev, int64_t n, void* stream);
 
+/* Fused Heun step around RAW network outputs F (what the fused trajectory launches between network
+ * evaluations; sampler_edm.py:350-367 with diffusion.py:60-63 inlined):
+ *   mid : D1 = clamp(c_skip(s) x + c_out(s) F1) ; d = (x - D1)/s ; x1 = x + h d        reads 8 B, writes 8 B / element
+ *   post: x1 = x + h d ; D2 = clamp(c_skip(s1) x1 + c_out(s1) F2) ; d2 = (x1 - D2)/s1 ;
+ *         x_next = x + h/2 (d + d2)                                                     reads 12 B, writes 4 B / element */
+int adb_edm_heun_mid(const float* x_dev, const float* f1_dev, float sigma, float sigma_data, float h, float* d_dev,
+                     float* x1_dev, int64_t n, void* stream);
+int adb_edm_heun_post(const float* x_dev, const float* d_dev, const float* f2_dev, float sigma1, float sigma_data, float h,
+                      float* x_next_dev, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Training twin — src/models/components/diffusion.py:65-97 (Diffusion.forward).
  * ---------------------------------------------------------------------------------------------- */

@@ -161,3 +161,24 @@ def test_dsm_loss(env):
     got = EluDiffusion(0.2)(x.to(dev), net_gpu, sigmas=sig.to(dev), noise=noise.to(dev))
     assert torch.allclose(got.cpu(), want, rtol=2e-5)
     N.check_async()
+
+
+@pytest.mark.parametrize("n", [1, 1003, 64000])
+def test_fused_heun_mid_post(env, n):
+    """adb_edm_heun_mid / adb_edm_heun_post (what the fused trajectory launches between network evaluations)
+    against one oracle Heun step written on raw network outputs."""
+    N, edm, dev = env
+    sd, s0, s1 = 0.2, 3.0, 1.7
+    x, f1, f2 = _rand((1, 1, n), 20, 3.0), _rand((1, 1, n), 21), _rand((1, 1, n), 22)
+    fs = iter([f1, f2])
+    want = edm.edm_sampler(x / s0, lambda xx, s: edm.denoise(xx, lambda a, b, **kw: next(fs), sd, sigma=float(s)),
+                           torch.tensor([s0, s1]), 1)
+    # one step s0 -> s1 of a two-entry schedule is Heun (s1 != 0); edm_sampler scales the noise by sig[0]
+    lib, st = N.lib(), N.stream_ptr(dev)
+    xd, f1d, f2d = x.to(dev), f1.to(dev), f2.to(dev)
+    d, x1, out = torch.empty_like(xd), torch.empty_like(xd), torch.empty_like(xd)
+    h = N.ctypes.c_float(N.ctypes.c_float(s1).value - N.ctypes.c_float(s0).value).value
+    N.check(lib.adb_edm_heun_mid(N.ptr(xd), N.ptr(f1d), s0, sd, h, N.ptr(d), N.ptr(x1), n, st))
+    N.check(lib.adb_edm_heun_post(N.ptr(xd), N.ptr(d), N.ptr(f2d), s1, sd, h, N.ptr(out), n, st))
+    N.check_async()
+    assert rel_l2(out, want) < 1e-6
