@@ -7,11 +7,13 @@ Drop-in `_target_`s (reference path -> this package):
     src.models.components.scheduler.KarrasSchedule        -> audiodiffuser_b200.components.scheduler.KarrasSchedule
     src.models.components.distribution.LogNormalDistribution -> audiodiffuser_b200.components.distribution.LogNormalDistribution
     src.models.backbones.wavenet.WaveNetNoise             -> audiodiffuser_b200.backbones.wavenet.WaveNetNoise
+    src.models.backbones.unet1d.UNet1dBase                -> audiodiffuser_b200.backbones.unet1d.UNet1dBase
 """
 from .components.diffusion import EluDiffusion, Diffusion              # noqa: F401
 from .components.sampler_edm import EDMSampler, EDMAlphaSampler        # noqa: F401
 from .components.scheduler import KarrasSchedule                        # noqa: F401
 from .components.distribution import LogNormalDistribution              # noqa: F401
 from .backbones.wavenet import WaveNetNoise, EDMDenoiser                # noqa: F401
+from .backbones.unet1d import UNet1dBase                                # noqa: F401
 
 __version__ = "0.1.0"

@@ -52,6 +52,19 @@ _SIGS = {
     "adb_wavenet_sample_edm": (c_int, [c_void_p, c_void_p, _F, c_int, c_int, c_float, c_float, c_float, c_float,
                                        c_float, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_int64, POINTER(c_int), c_void_p]),
+    "adb_cl_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_conv_packed_elems": (c_int64, [c_int, c_int, c_int]),
+    "adb_cl_pack_conv_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_time_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "adb_cl_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_float, c_int, c_int, c_void_p]),
+    "adb_cl_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "adb_cl_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_concat": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_wavenc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_wavdec": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_wavenet_set_timing": (c_int, [c_void_p, c_int]),
     "adb_wavenet_timers": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
 }

@@ -19,6 +19,8 @@
 #include "wavenet_f32.cuh"
 #include "wavenet_tc.cuh"
 #include "wavenet_tc2.cuh"
+#include "cl_ops.cuh"
+#include "cl_conv_tc.cuh"
 
 using namespace adb;
 
@@ -960,3 +962,5 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
     if (nfe_out) *nfe_out = nfe;
     return ADB_OK;
 }
+
+#include "cl_api.inc"

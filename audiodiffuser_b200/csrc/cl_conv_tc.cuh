@@ -1,0 +1,200 @@
+// Tensor-core (tcgen05 / TMEM / TMA) version of the generic channels-last GEMM-convolution of cl_ops.cuh:
+// bf16 activations [B][L][C], bf16 weights, fp32 accumulation in TMEM, fused bias / activation / residual epilogue.
+// Used for every convolution and 1x1 / Linear layer of the U-Net whose K (= Cin per tap) is a multiple of 64
+// (unet1d.py: ConvBlock1d.project :186-193, ResnetBlock1d.to_out :291-295, Downsample1d :214-225, Upsample1d
+// :246-255, FeedForward1d :49-61, Attention projections attention_utils.py:95-110).
+//
+// One persistent CTA per SM walks (m-tile, n-tile) pairs: M = 128 rows of one sample, N tile = 64 / 128 / 256
+// columns. Per K-block (64 input channels of one tap) the producer warp TMA-loads the activation box
+// [128 rows][64 ch] at row offset off0 + tap*dil (out-of-range rows are zero-filled by TMA = the conv's zero
+// padding) and the weight box [NT][64]; one thread issues 4 tcgen05.mma (K = 16 each). Two TMEM accumulators
+// alternate between tiles so a tile's epilogue overlaps the next tile's MMAs.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+#include "cl_ops.cuh"
+
+namespace adb {
+
+constexpr int CT_STAGES = 4;
+constexpr int CT_A_BYTES = 128 * 64 * 2;            // 16 KB
+constexpr int CT_B_BYTES = 256 * 64 * 2;            // 32 KB (NT = 256; smaller tiles use a prefix)
+constexpr int CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
+constexpr int CT_THREADS = 192;                     // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 1024 /*bias*/ + 16 * 8 + 16;
+
+enum CtWaitSite : uint32_t { SITE_CT_EMPTY = 20, SITE_CT_FULL = 21, SITE_CT_TEMPTY = 22, SITE_CT_TFULL = 23 };
+
+struct ClConvTcParams {
+    ClConvArgs a;
+    int NT;                 // N tile (64, 128 or 256)
+    int tiles_per_b;        // ceil(rows / 128)
+    int tiles_m;            // B * tiles_per_b
+    int tiles_n;            // N / NT
+    int kb_per_tap;         // Cin / 64
+};
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const ClConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_bias = reinterpret_cast<float*>(smem + CT_STAGES * CT_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CT_STAGES * CT_STAGE_BYTES + 1024);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + CT_STAGES;
+    uint64_t* bar_tfull = bars + 2 * CT_STAGES;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ClConvArgs& a = p.a;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_in); tma_prefetch_desc(&tm_w); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(s_tmem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+    const int nkb = a.taps * p.kb_per_tap;
+    const int total_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t stage_tx = CT_A_BYTES + static_cast<uint32_t>(p.NT) * 128u;
+
+    if (warp == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int b = tm / p.tiles_per_b, t0 = (tm % p.tiles_per_b) * 128, n0 = tn * p.NT;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&bar_empty[stage], phase ^ 1, SITE_CT_EMPTY, stage);
+                if (lane == 0) {
+                    uint8_t* sa = smem + stage * CT_STAGE_BYTES;
+                    const int tap = kb / p.kb_per_tap, cib = kb % p.kb_per_tap;
+                    mbar_arrive_expect_tx(&bar_full[stage], stage_tx);
+                    tma_load_3d(sa, &tm_in, &bar_full[stage], cib * 64, t0 + a.off0 + tap * a.dil, b);
+                    tma_load_2d(sa + CT_A_BYTES, &tm_w, &bar_full[stage], 0, kb * a.N + n0);
+                }
+                __syncwarp();
+                if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        uint32_t stage = 0, phase = 0, it = 0;
+        const uint32_t idesc = umma_idesc_bf16_f32(128, static_cast<uint32_t>(p.NT));
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1, use = it >> 1;
+            mbar_wait(&bar_tempty[buf], (use & 1) ^ 1, SITE_CT_TEMPTY, buf);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + buf * 256;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&bar_full[stage], phase, SITE_CT_FULL, stage);
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * CT_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(d_tmem, umma_desc_sw128_kmajor(sa + k * 32), umma_desc_sw128_kmajor(sa + CT_A_BYTES + k * 32),
+                                     idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&bar_empty[stage]);
+                    if (kb == nkb - 1) umma_commit(&bar_tfull[buf]);
+                }
+                __syncwarp();
+                if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+        const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(a.res);
+        uint32_t it = 0;
+        int cur_n0 = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int b = tm / p.tiles_per_b, t = (tm % p.tiles_per_b) * 128 + row, n0 = tn * p.NT;
+            const uint32_t buf = it & 1, use = it >> 1;
+            if (n0 != cur_n0) {                     // bias slice of this n-tile (epilogue warps only: named barrier 1)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x - 64; i < p.NT; i += 128) s_bias[i] = a.bias ? a.bias[n0 + i] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_n0 = n0;
+            }
+            mbar_wait(&bar_tfull[buf], use & 1, SITE_CT_TFULL, buf);
+            tc_fence_after_sync();
+            const bool row_ok = t < a.rows;
+            for (int cc = 0; cc < p.NT / 32; ++cc) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_lane + buf * 256 + cc * 32, r);
+                tmem_ld_wait();
+                const int n = n0 + cc * 32;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = cl_act(__uint_as_float(r[i]) + s_bias[cc * 32 + i], a.act);
+                long long o;
+                bool ok = row_ok;
+                if (a.ups == 0) {
+                    o = (static_cast<long long>(b) * a.rows + t) * a.N + n;
+                    if (res && ok) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res + o);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const uint4 u = rp[m];
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[8 * m + 2 * e] += __uint_as_float(w[e] << 16);
+                                v[8 * m + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                            }
+                        }
+                    }
+                } else {
+                    const int cout = a.N / a.ups, ph = n / cout, c = n % cout;
+                    const int to = t * a.ups + ph - a.shift;
+                    ok = ok && to >= 0 && to < a.L_out;
+                    o = (static_cast<long long>(b) * a.L_out + to) * cout + c;
+                }
+                if (ok) {
+                    uint4* op = reinterpret_cast<uint4*>(out + o);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        op[m] = make_uint4(pack_bf16x2(v[8 * m], v[8 * m + 1]), pack_bf16x2(v[8 * m + 2], v[8 * m + 3]),
+                                           pack_bf16x2(v[8 * m + 4], v[8 * m + 5]), pack_bf16x2(v[8 * m + 6], v[8 * m + 7]));
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// fp32 [taps][Cin][N] -> bf16 blocks [kb = tap * Cin/64 + cib][N][64] (K-major rows of 128 bytes, what one TMA box
+// with the 128-byte swizzle loads)
+__global__ void cl_pack_conv_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int N, int taps) {
+    const long long total = static_cast<long long>(taps) * Cin * N;
+    const int kbt = Cin / 64;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i & 63);
+        const int n = static_cast<int>((i >> 6) % N);
+        const int kb = static_cast<int>(i / (64LL * N));
+        const int tap = kb / kbt, cib = kb % kbt;
+        out[i] = __float2bfloat16_rn(w[(static_cast<long long>(tap) * Cin + cib * 64 + k) * N + n]);
+    }
+}
+
+}  // namespace adb

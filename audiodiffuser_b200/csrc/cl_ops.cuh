@@ -1,0 +1,375 @@
+// Channels-last building blocks of the 1-D U-Net backbone (fp32 CUDA-core path + shared small kernels).
+//
+// Reference: src/models/backbones/unet1d.py — ConvBlock1d :163-207 (GroupNorm -> scale/shift -> SiLU -> conv),
+// ResnetBlock1d :257-316, Downsample1d / Upsample1d :214-255, WAVenc1d / WAVdec1d :572-622, LayerNorm /
+// LayerNorm1d :16-45, FeedForward1d :49-61, TransformerBlock1d :67-122, time embedding :128-148;
+// src/models/backbones/attention_utils.py:78-184 (self-attention branch).
+//
+// Activations are channels-last [B][L][C] (the reference is [B][C][L]); T = float (fp32 path) or
+// __nv_bfloat16 (tensor-core path, statistics and softmax still in fp32). Every convolution of the network is
+// expressed as ONE generic "GEMM-convolution"
+//     Y[b][t][n] = act( bias[n] + sum_{j < taps} sum_{ci} X[b][t + off0 + j*dil][ci] * W[j][ci][n] ) (+ res[b][t][n])
+// with rows of X outside [0, L_in) reading as zero (the conv's zero padding):
+//   * k=3 "same" conv            taps 3, off0 -1, dil 1
+//   * 1x1 conv / Linear          taps 1
+//   * strided conv k=2f+1,s=f,p=f  on the free view [L/f][f*Cin]: taps 3, off0 -1, unused fine taps have zero weights
+//   * ConvTranspose k=2f,s=f     taps 2, off0 0, dil -1, N = f*Cout, rows = L_in + 1, and the store maps
+//                                (t, n) -> output row t*f + n/Cout - p, channel n % Cout (each output sample is the sum
+//                                of exactly two (input row, tap) products, so no overlap-add pass is needed)
+#pragma once
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+
+namespace adb {
+
+enum ClAct : int { CL_ACT_NONE = 0, CL_ACT_RELU = 1, CL_ACT_SILU = 2, CL_ACT_GELU = 3 };
+
+__device__ __forceinline__ float cl_act(float x, int act) {
+    switch (act) {
+        case CL_ACT_RELU: return fmaxf(x, 0.f);
+        case CL_ACT_SILU: return x / (1.0f + expf(-x));
+        case CL_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));   // nn.GELU() default (erf)
+        default: return x;
+    }
+}
+
+template <typename T> __device__ __forceinline__ float cl_ld(const T* p);
+template <> __device__ __forceinline__ float cl_ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float cl_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void cl_st(T* p, float v);
+template <> __device__ __forceinline__ void cl_st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void cl_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+struct ClConvArgs {
+    const void* in;      // [B][L_in][Cin]
+    const void* w;       // fp32 path: [taps][Cin][N] fp32 ; tensor-core path: packed blocks (cl_conv_tc.cuh)
+    const float* bias;   // [N] or nullptr
+    const void* res;     // [B][rows][N] or nullptr (normal store only)
+    void* out;           // normal: [B][rows][N] ; transposed: [B][L_out][N / ups]
+    int B, L_in, rows, Cin, N, taps, off0, dil, act;
+    int ups;             // 0: normal store ; f > 0: transposed store with N = f * Cout
+    int shift, L_out;    // transposed store: output row = t * ups + n / Cout - shift, kept if in [0, L_out)
+};
+
+// fp32 tiled GEMM: 64 (rows) x 64 (n) x 16 (k), 256 threads, 4x4 outputs per thread. Cin % 16 == 0, N % 64 == 0.
+__global__ void __launch_bounds__(256) cl_conv_f32_kernel(ClConvArgs p) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN];
+    const int b = blockIdx.z, t0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    float acc[4][4] = {};
+    const float* inb = static_cast<const float*>(p.in) + static_cast<long long>(b) * p.L_in * p.Cin;
+    const float* w = static_cast<const float*>(p.w);
+    const int ksteps = p.taps * p.Cin / BK;
+    const int a_row = tid / 4, a_k = (tid % 4) * 4;
+    const int b_k = tid / 16, b_c = (tid % 16) * 4;
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const int kglob = ks * BK, tap = kglob / p.Cin, ci0 = kglob % p.Cin;
+        {
+            const int t = t0 + a_row;
+            const int s = t + p.off0 + tap * p.dil;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < p.rows && s >= 0 && s < p.L_in)
+                v = *reinterpret_cast<const float4*>(inb + static_cast<long long>(s) * p.Cin + ci0 + a_k);
+            As[a_k + 0][a_row] = v.x; As[a_k + 1][a_row] = v.y; As[a_k + 2][a_row] = v.z; As[a_k + 3][a_row] = v.w;
+        }
+        *reinterpret_cast<float4*>(&Bs[b_k][b_c]) =
+            *reinterpret_cast<const float4*>(w + static_cast<long long>(kglob + b_k) * p.N + n0 + b_c);
+        __syncthreads();
+        float part[4][4] = {};      // per-slice partial sums keep the rounding error ~ K/16 + 16 terms
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
+        __syncthreads();
+    }
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    const int n = n0 + tx * 4;
+    if (p.bias) { const float4 bb = *reinterpret_cast<const float4*>(p.bias + n); bias[0] = bb.x; bias[1] = bb.y; bias[2] = bb.z; bias[3] = bb.w; }
+    float* out = static_cast<float*>(p.out);
+    const float* res = static_cast<const float*>(p.res);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + ty * 4 + i;
+        if (t >= p.rows) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = cl_act(acc[i][j] + bias[j], p.act);
+        if (p.ups == 0) {
+            const long long o = (static_cast<long long>(b) * p.rows + t) * p.N + n;
+            if (res) { const float4 r = *reinterpret_cast<const float4*>(res + o); v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w; }
+            *reinterpret_cast<float4*>(out + o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            const int cout = p.N / p.ups, phase = n / cout, c = n % cout;
+            const int to = t * p.ups + phase - p.shift;
+            if (to >= 0 && to < p.L_out)
+                *reinterpret_cast<float4*>(out + (static_cast<long long>(b) * p.L_out + to) * cout + c) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small dense layers on [B][K] rows (time embedding MLP, per-block conditioning projections):
+//   out[b][n] = bias[n] + sum_k W[n][k] * f(in[b][k]),  f = SiLU if silu_in (unet1d.py:271-276), W in torch layout
+// One warp per output element.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cl_linear_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out, int B, int K,
+                                                        int N, int silu_in, int act) {
+    const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= static_cast<long long>(B) * N) return;
+    const int b = static_cast<int>(warp / N), n = static_cast<int>(warp % N);
+    const float* x = in + static_cast<long long>(b) * K;
+    const float* wr = w + static_cast<long long>(n) * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float v = x[k];
+        if (silu_in) v = v / (1.0f + expf(-v));
+        acc = fmaf(wr[k], v, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[warp] = cl_act(acc + (bias ? bias[n] : 0.f), act);
+}
+
+// [t, sin(2 pi t w_j), cos(2 pi t w_j)]   (LearnedPositionalEmbedding, unet1d.py:128-142). out: [B][2*half + 1]
+__global__ void cl_time_features_kernel(const float* __restrict__ t, const float* __restrict__ w, float* __restrict__ out,
+                                        int B, int half) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int width = 2 * half + 1;
+    if (i >= B * width) return;
+    const int b = i / width, j = i % width;
+    const float x = t[b];
+    if (j == 0) { out[i] = x; return; }
+    const int jj = (j - 1) % half;
+    const float f = __fmul_rn(__fmul_rn(__fmul_rn(x, w[jj]), 2.0f), 3.14159265358979323846f);   // x * w * 2 * pi, left to right
+    out[i] = (j - 1 < half) ? sinf(f) : cosf(f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm (nn.GroupNorm(num_groups, C), unet1d.py:179) over (C/G channels x L) per sample.
+//   pass 1: fp64 sum / sum of squares per (b, g) -> sums[b][g][2] (zeroed by the caller)
+//   pass 2: y = (x - mean) * rstd * gamma + beta ; optional y = y * (scale + 1) + shift (unet1d.py:160-161) ; act
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cl_gn_stats_kernel(const T* __restrict__ in, double* __restrict__ sums, int L, int C,
+                                                          int G, int chunks) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cpg = C / G;
+    const int rows_per = (L + chunks - 1) / chunks;
+    const int r0 = chunk * rows_per, r1 = min(L, r0 + rows_per);
+    if (r0 >= r1) return;
+    const T* base = in + static_cast<long long>(b) * L * C;
+    __shared__ double red[2][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = 0; g < G; ++g) {
+        double s = 0.0, ss = 0.0;
+        const long long n = static_cast<long long>(r1 - r0) * cpg;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const int r = r0 + static_cast<int>(i / cpg), j = static_cast<int>(i % cpg);
+            const double v = static_cast<double>(cl_ld<T>(base + static_cast<long long>(r) * C + g * cpg + j));
+            s += v;
+            ss += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, c = 0.0;
+            for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += red[0][w]; c += red[1][w]; }
+            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2], a);
+            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2 + 1], c);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cl_gn_apply_kernel(const T* __restrict__ in, const double* __restrict__ sums,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ ss, long long ss_ld, T* __restrict__ out,
+                                                          int B, int L, int C, int G, float eps, int act) {
+    const long long total = static_cast<long long>(B) * L * C;
+    const int cpg = C / G;
+    const double cnt = static_cast<double>(cpg) * L;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const int b = static_cast<int>(i / (static_cast<long long>(L) * C));
+        const double* sp = sums + (static_cast<long long>(b) * G + c / cpg) * 2;
+        const double mean = sp[0] / cnt;
+        const double var = fmax(sp[1] / cnt - mean * mean, 0.0);
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        float y = (cl_ld<T>(in + i) - static_cast<float>(mean)) * rstd * gamma[c] + beta[c];
+        if (ss) {
+            const float* sb = ss + static_cast<long long>(b) * ss_ld;
+            y = y * (sb[c] + 1.0f) + sb[C + c];
+        }
+        cl_st<T>(out + i, cl_act(y, act));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim of each [C] row (nn.LayerNorm(C) unet1d.py:79 with gain+bias; LayerNorm1d
+// unet1d.py:32-45 with gain only — in channels-last both are the same row-wise op). One warp per row.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cl_layernorm_kernel(const T* __restrict__ in, const float* __restrict__ g,
+                                                           const float* __restrict__ bvec, T* __restrict__ out, long long rows,
+                                                           int C, float eps) {
+    const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const T* x = in + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += cl_ld<T>(x + c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = cl_ld<T>(x + c) - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / C + eps);
+    for (int c = lane; c < C; c += 32) {
+        float y = (cl_ld<T>(x + c) - mean) * rstd * g[c];
+        if (bvec) y += bvec[c];
+        cl_st<T>(out + row * C + c, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-attention core (attention_utils.py:163-184): per (batch, head) softmax(q k^T d^-1/2) v with the softmax in
+// fp32. q: [B][L][C], kv: [B][L][2C] (k = first C columns, v = last C), out: [B][L][C]; head h owns columns
+// [h*d, (h+1)*d). K and V of one (b, h) live in shared memory; one warp per query row.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cl_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out,
+                                                           int L, int C, int heads) {
+    extern __shared__ float smem_att[];
+    const int d = C / heads;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    float* Ks = smem_att;                       // [L][d + 1]
+    float* Vs = Ks + static_cast<size_t>(L) * (d + 1);   // [L][d]
+    float* Ps = Vs + static_cast<size_t>(L) * d;         // [warps][L]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const T* kvb = kv + static_cast<long long>(b) * L * 2 * C;
+    for (int i = threadIdx.x; i < L * d; i += blockDim.x) {
+        const int r = i / d, c = i % d;
+        Ks[r * (d + 1) + c] = cl_ld<T>(kvb + static_cast<long long>(r) * 2 * C + h * d + c);
+        Vs[r * d + c] = cl_ld<T>(kvb + static_cast<long long>(r) * 2 * C + C + h * d + c);
+    }
+    __syncthreads();
+    const float scale = rsqrtf(static_cast<float>(d));
+    float* P = Ps + static_cast<size_t>(warp) * L;
+    for (int qi = blockIdx.y * nwarps + warp; qi < L; qi += gridDim.y * nwarps) {
+        const T* qr = q + (static_cast<long long>(b) * L + qi) * C + h * d;
+        float mx = -INFINITY;
+        for (int j = lane; j < L; j += 32) {
+            float s = 0.f;
+            for (int c = 0; c < d; ++c) s = fmaf(cl_ld<T>(qr + c), Ks[j * (d + 1) + c], s);
+            s *= scale;
+            P[j] = s;
+            mx = fmaxf(mx, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < L; j += 32) { const float e = expf(P[j] - mx); P[j] = e; sum += e; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncwarp();
+        const float inv = 1.0f / sum;
+        for (int c = lane; c < d; c += 32) {
+            float acc = 0.f;
+            for (int j = 0; j < L; ++j) acc = fmaf(P[j] * inv, Vs[j * d + c], acc);
+            cl_st<T>(out + (static_cast<long long>(b) * L + qi) * C + h * d + c, acc);
+        }
+        __syncwarp();
+    }
+}
+
+// out[r][0:Ca] = a[r][:], out[r][Ca:Ca+Cb] = b[r][:] * scale_b   (UpsampleBlock1d.add_skip, unet1d.py:536-537)
+template <typename T>
+__global__ void __launch_bounds__(256) cl_concat_kernel(const T* __restrict__ a, const T* __restrict__ bsrc, float scale_b,
+                                                        T* __restrict__ out, long long rows, int Ca, int Cb) {
+    const int Ct = Ca + Cb;
+    const long long total = rows * Ct;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / Ct;
+        const int c = static_cast<int>(i % Ct);
+        if (c < Ca) out[i] = a[r * Ca + c];
+        else cl_st<T>(out + i, cl_ld<T>(bsrc + r * Cb + (c - Ca)) * scale_b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WAVenc1d (unet1d.py:572-594): x [B][Cin][L] channels-FIRST fp32 -> h [B][L/S][F] channels-last,
+//   h[b][t][f] = sum_{c,k} w[f][c][k] * x[b][c][t*S + k - pad],  pad = W/2 - S/2, no bias. Cin*W is tiny (64).
+// WAVdec1d (unet1d.py:596-622): h [B][Lc][F] channels-last -> y [B][Cout][Lc*S] channels-first fp32,
+//   y[b][c][t] = sum_f sum_{i,k: i*S + k - pad = t} h[b][i][f] * w[f][c][k]   (two (i, k) pairs per t when W = 2S)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cl_wavenc_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ out,
+                                                        int B, int Cin, int L, int F, int W, int S, int pad) {
+    const int Lc = (L + 2 * pad - W) / S + 1;
+    const long long total = static_cast<long long>(B) * Lc * F;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int f = static_cast<int>(i % F);
+        const int t = static_cast<int>((i / F) % Lc);
+        const int b = static_cast<int>(i / (static_cast<long long>(F) * Lc));
+        float acc = 0.f;
+        for (int c = 0; c < Cin; ++c) {
+            const float* xr = x + (static_cast<long long>(b) * Cin + c) * L;
+            const float* wr = w + (static_cast<long long>(f) * Cin + c) * W;
+            for (int k = 0; k < W; ++k) {
+                const int s = t * S + k - pad;
+                if (s >= 0 && s < L) acc = fmaf(wr[k], xr[s], acc);
+            }
+        }
+        cl_st<T>(out + i, acc);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cl_wavdec_kernel(const T* __restrict__ h, const float* __restrict__ w, float* __restrict__ y,
+                                                        int B, int Lc, int F, int Cout, int W, int S, int pad) {
+    const int L = (Lc - 1) * S - 2 * pad + W;
+    const long long total = static_cast<long long>(B) * Cout * L;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i % L);
+        const int c = static_cast<int>((i / L) % Cout);
+        const int b = static_cast<int>(i / (static_cast<long long>(L) * Cout));
+        float acc = 0.f;
+        // k = t + pad - i*S in [0, W)
+        const int u = t + pad;
+        for (int ii = u / S; ii >= 0 && u - ii * S < W; --ii) {
+            if (ii >= Lc) continue;
+            const int k = u - ii * S;
+            const T* hr = h + (static_cast<long long>(b) * Lc + ii) * F;
+            for (int f = 0; f < F; ++f) acc = fmaf(cl_ld<T>(hr + f), w[(static_cast<long long>(f) * Cout + c) * W + k], acc);
+        }
+        y[i] = acc;
+    }
+}
+
+}  // namespace adb

@@ -146,6 +146,59 @@ int adb_wavenet_sample_edm(adb_wavenet* net, const float* noise_dev, const float
 int adb_wavenet_set_timing(adb_wavenet* net, int enabled);
 int adb_wavenet_timers(adb_wavenet* net, double* ms_out /*[ADB_TIMER_COUNT]*/, int64_t* launches_out /*[ADB_TIMER_COUNT]*/);
 
+/* ------------------------------------------------------------------------------------------------
+ * 1-D U-Net building blocks — src/models/backbones/unet1d.py, src/models/backbones/attention_utils.py.
+ * Activations are channels-last [B][L][C] in `dtype` (ADB_DTYPE_F32: CUDA-core fp32 path, <= 1e-5 relative;
+ * ADB_DTYPE_BF16: tcgen05 path with bf16 activations / weights, fp32 accumulate, statistics and softmax in fp32).
+ * The host side (audiodiffuser_b200/backbones/unet1d.py) sequences these exactly like UNet1d.forward
+ * (unet1d.py:769-816).
+ * ---------------------------------------------------------------------------------------------- */
+#define ADB_DTYPE_F32 0
+#define ADB_DTYPE_BF16 1
+#define ADB_ACT_NONE 0
+#define ADB_ACT_RELU 1
+#define ADB_ACT_SILU 2
+#define ADB_ACT_GELU 3   /* erf form, nn.GELU() default (unet1d.py:55) */
+
+/* Generic channels-last GEMM-convolution (nn.Conv1d / nn.ConvTranspose1d / bias-free nn.Linear call sites:
+ * unet1d.py:154-158, :186-193, :214-255, :291-295, :49-61; attention_utils.py:95-110):
+ *   Y[b][t][n] = act(bias[n] + sum_{j<taps} sum_{ci} X[b][t + off0 + j*dil][ci] * W[j][ci][n]) (+ res[b][t][n]),
+ *   t in [0, rows), rows of X outside [0, L_in) read as zero.
+ * ups == 0: out is [B][rows][N]. ups = f > 0 (ConvTranspose k = 2f, s = f): N = f*Cout and (t, n) is stored to
+ * output row t*f + n/Cout - shift (kept if in [0, L_out)), channel n % Cout of out [B][L_out][Cout].
+ * w: ADB_DTYPE_F32 -> fp32 [taps][Cin][N]; ADB_DTYPE_BF16 -> blocks written by adb_cl_pack_conv_weights. */
+int adb_cl_conv(const void* in_dev, const void* w_dev, const float* bias_dev, const void* res_dev, void* out_dev, int B,
+                int L_in, int rows, int Cin, int N, int taps, int off0, int dil, int act, int ups, int shift, int L_out,
+                int dtype, void* stream);
+int64_t adb_cl_conv_packed_elems(int Cin, int N, int taps);
+int adb_cl_pack_conv_weights(const float* w_f32_dev, void* packed_bf16_dev, int Cin, int N, int taps, void* stream);
+/* out[b][n] = act(bias[n] + sum_k W[n][k] * f(in[b][k])), f = SiLU if silu_in; fp32 (time MLP unet1d.py:678-684,
+ * to_cond_embedding :271-276, :304-308) */
+int adb_cl_linear(const float* in_dev, const float* w_dev, const float* bias_dev, float* out_dev, int B, int K, int N,
+                  int silu_in, int act, void* stream);
+/* [t, sin(2 pi t w), cos(2 pi t w)] -> out [B][2*half+1]   (LearnedPositionalEmbedding, unet1d.py:128-142) */
+int adb_cl_time_features(const float* t_dev, const float* w_dev, float* out_dev, int B, int half, void* stream);
+/* nn.GroupNorm(G, C) + optional x*(scale+1)+shift (scale_shift_dev [B][ss_ld]: scale at [0,C), shift at [C,2C)) +
+ * activation   (ConvBlock1d.forward, unet1d.py:195-207). sums_ws_dev: [B][G][2] doubles of scratch. */
+int adb_cl_groupnorm(const void* in_dev, const float* gamma_dev, const float* beta_dev, const float* scale_shift_dev,
+                     int64_t ss_ld, void* out_dev, double* sums_ws_dev, int B, int L, int C, int G, float eps, int act,
+                     int dtype, void* stream);
+/* row-wise LayerNorm over C (nn.LayerNorm unet1d.py:79 with b_dev; LayerNorm1d unet1d.py:32-45 with b_dev = NULL) */
+int adb_cl_layernorm(const void* in_dev, const float* g_dev, const float* b_dev, void* out_dev, int64_t rows, int C, float eps,
+                     int dtype, void* stream);
+/* softmax(q k^T / sqrt(d)) v per (batch, head); q [B][L][C], kv [B][L][2C] (k | v)   (attention_utils.py:163-184) */
+int adb_cl_attention(const void* q_dev, const void* kv_dev, void* out_dev, int B, int L, int C, int heads, int dtype,
+                     void* stream);
+/* out = [a | scale_b * b] along channels   (UpsampleBlock1d.add_skip, unet1d.py:536-537) */
+int adb_cl_concat(const void* a_dev, const void* b_dev, float scale_b, void* out_dev, int64_t rows, int Ca, int Cb, int dtype,
+                  void* stream);
+/* WAVenc1d (unet1d.py:572-594): x [B][Cin][L] fp32 channels-first -> [B][L/S][F] channels-last in `dtype`;
+ * WAVdec1d (unet1d.py:596-622): [B][Lc][F] -> y [B][Cout][Lc*S] fp32 channels-first. w in torch layout. */
+int adb_cl_wavenc(const float* x_dev, const float* w_dev, void* out_dev, int B, int Cin, int L, int F, int W, int S, int dtype,
+                  void* stream);
+int adb_cl_wavdec(const void* h_dev, const float* w_dev, float* y_dev, int B, int Lc, int F, int Cout, int W, int S, int dtype,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
