@@ -137,7 +137,7 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                 const int n = n0 + cc * 32;
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = cl_act(__uint_as_float(r[i]) + s_bias[cc * 32 + i], a.act);
+                for (int i = 0; i < 32; ++i) v[i] = cl_act_fast(__uint_as_float(r[i]) + s_bias[cc * 32 + i], a.act);
                 long long o;
                 bool ok = row_ok;
                 if (a.ups == 0) {

@@ -33,6 +33,19 @@ __device__ __forceinline__ float cl_act(float x, int act) {
     }
 }
 
+// bf16 paths: MUFU-based exp / reciprocal (error ~1e-6 relative, far below the bf16 rounding of the result)
+__device__ __forceinline__ float cl_act_fast(float x, int act) {
+    switch (act) {
+        case CL_ACT_RELU: return fmaxf(x, 0.f);
+        case CL_ACT_SILU: return __fdividef(x, 1.0f + __expf(-x));
+        case CL_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+        default: return x;
+    }
+}
+template <typename T> __device__ __forceinline__ float cl_act_t(float x, int act);
+template <> __device__ __forceinline__ float cl_act_t<float>(float x, int act) { return cl_act(x, act); }
+template <> __device__ __forceinline__ float cl_act_t<__nv_bfloat16>(float x, int act) { return cl_act_fast(x, act); }
+
 template <typename T> __device__ __forceinline__ float cl_ld(const T* p);
 template <> __device__ __forceinline__ float cl_ld<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float cl_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
@@ -369,6 +382,232 @@ __global__ void __launch_bounds__(256) cl_wavdec_kernel(const T* __restrict__ h,
             for (int f = 0; f < F; ++f) acc = fmaf(cl_ld<T>(hr + f), w[(static_cast<long long>(f) * Cout + c) * W + k], acc);
         }
         y[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast paths (memory-bound, 128-bit vectorised) used when the shapes allow; the simple kernels above stay as
+// the general fallback.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct ClVec;
+template <> struct ClVec<float> {
+    static constexpr int N = 4;
+    __device__ static void load(const float* p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    __device__ static void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct ClVec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+    }
+    __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+};
+
+// GroupNorm statistics, one pass: thread owns one 16-byte channel vector (fixed group) and strides over the rows of
+// its chunk (4 independent loads in flight); fp32 partial sums over <= 16 rows are promoted to fp64; the block
+// combines per group with warp shuffles (fp64) and issues 2 global atomics per group.
+// Needs (C / G) % VEC == 0, 256 % (C / VEC) == 0, (256 / G) threads per group. grid (chunks, B).
+template <typename T>
+__global__ void __launch_bounds__(256) cl_gn_stats_vec_kernel(const T* __restrict__ in, double* __restrict__ sums, int L, int C,
+                                                              int G, int chunks) {
+    constexpr int VE = ClVec<T>::N;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cpg = C / G, vpr = C / VE;
+    const int rows_per = (L + chunks - 1) / chunks;
+    const int r0 = chunk * rows_per, r1 = min(L, r0 + rows_per);
+    __shared__ double sd[2][256];
+    const T* base = in + static_cast<long long>(b) * L * C;
+    const int rstep = 256 / vpr, rofs = threadIdx.x / vpr, v = threadIdx.x % vpr;
+    double ds = 0.0, dss = 0.0;
+    {
+        const T* col = base + v * VE;
+        int r = r0 + rofs;
+        for (; r + 3 * rstep < r1; r += 4 * rstep) {
+            float x0[VE], x1[VE], x2[VE], x3[VE];
+            ClVec<T>::load(col + static_cast<long long>(r) * C, x0);
+            ClVec<T>::load(col + static_cast<long long>(r + rstep) * C, x1);
+            ClVec<T>::load(col + static_cast<long long>(r + 2 * rstep) * C, x2);
+            ClVec<T>::load(col + static_cast<long long>(r + 3 * rstep) * C, x3);
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < VE; ++i) {
+                s0 += x0[i] + x1[i]; q0 = fmaf(x0[i], x0[i], fmaf(x1[i], x1[i], q0));
+                s1 += x2[i] + x3[i]; q1 = fmaf(x2[i], x2[i], fmaf(x3[i], x3[i], q1));
+            }
+            ds += static_cast<double>(s0 + s1);
+            dss += static_cast<double>(q0 + q1);
+        }
+        for (; r < r1; r += rstep) {
+            float x0[VE];
+            ClVec<T>::load(col + static_cast<long long>(r) * C, x0);
+            float s0 = 0.f, q0 = 0.f;
+#pragma unroll
+            for (int i = 0; i < VE; ++i) { s0 += x0[i]; q0 = fmaf(x0[i], x0[i], q0); }
+            ds += static_cast<double>(s0);
+            dss += static_cast<double>(q0);
+        }
+    }
+    sd[0][threadIdx.x] = ds;
+    sd[1][threadIdx.x] = dss;
+    __syncthreads();
+    const int vg = cpg / VE;                       // vectors per group within a row
+    const int per = rstep * vg;                    // threads that accumulated into one group
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < G; g += 8) {
+        double a = 0.0, c = 0.0;
+        for (int j = lane; j < per; j += 32) {
+            const int idx = (j / vg) * vpr + g * vg + (j % vg);
+            a += sd[0][idx];
+            c += sd[1][idx];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2], a);
+            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2 + 1], c);
+        }
+    }
+}
+
+// GroupNorm apply: per-group mean / rstd are finished in fp64 by G threads, per-channel affine coefficients
+// (normalisation, gain / bias and the optional (scale + 1, shift) folded) are built once per block in shared memory,
+// then one vectorised fused pass. grid (chunks, B); C <= 2048, G <= 64.
+template <typename T>
+__global__ void __launch_bounds__(256) cl_gn_apply_vec_kernel(const T* __restrict__ in, const double* __restrict__ sums,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ ss, long long ss_ld, T* __restrict__ out,
+                                                              int L, int C, int G, float eps, int act, int chunks) {
+    constexpr int VE = ClVec<T>::N;
+    __shared__ float ca[2048], cb[2048];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int cpg = C / G;
+    if (threadIdx.x < G) {
+        const double cnt = static_cast<double>(cpg) * L;
+        const double* sp = sums + (static_cast<long long>(b) * G + threadIdx.x) * 2;
+        const double mean = sp[0] / cnt;
+        const double var = fmax(sp[1] / cnt - mean * mean, 0.0);
+        s_mean[threadIdx.x] = static_cast<float>(mean);
+        s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float a = s_rstd[g] * gamma[c];
+        float bb = beta[c] - s_mean[g] * a;
+        if (ss) {
+            const float sc = ss[static_cast<long long>(b) * ss_ld + c] + 1.0f, sh = ss[static_cast<long long>(b) * ss_ld + C + c];
+            a *= sc;
+            bb = fmaf(bb, sc, sh);
+        }
+        ca[c] = a; cb[c] = bb;
+    }
+    __syncthreads();
+    const int vpr = C / VE;
+    const int rows_per = (L + chunks - 1) / chunks;
+    const int r0 = chunk * rows_per, r1 = min(L, r0 + rows_per);
+    const int nvec = (r1 - r0) * vpr;               // < 2^31: rows_per * C / VE
+    const T* src = in + (static_cast<long long>(b) * L + r0) * C;
+    T* dst = out + (static_cast<long long>(b) * L + r0) * C;
+    // 256 % vpr == 0 or vpr % 256 == 0 (checked by the caller): a thread's channel offset only depends on tid
+    constexpr int UN = (VE == 4) ? 4 : 2;
+    int i = threadIdx.x;
+    for (; i + 256 * (UN - 1) < nvec; i += 256 * UN) {
+        float x[UN][VE];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) ClVec<T>::load(src + static_cast<long long>(i + 256 * u) * VE, x[u]);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int c0 = ((i + 256 * u) % vpr) * VE;
+#pragma unroll
+            for (int k = 0; k < VE; ++k) x[u][k] = cl_act_t<T>(fmaf(x[u][k], ca[c0 + k], cb[c0 + k]), act);
+            ClVec<T>::store(dst + static_cast<long long>(i + 256 * u) * VE, x[u]);
+        }
+    }
+    for (; i < nvec; i += 256) {
+        const int c0 = (i % vpr) * VE;
+        float x[VE];
+        ClVec<T>::load(src + static_cast<long long>(i) * VE, x);
+#pragma unroll
+        for (int k = 0; k < VE; ++k) x[k] = cl_act_t<T>(fmaf(x[k], ca[c0 + k], cb[c0 + k]), act);
+        ClVec<T>::store(dst + static_cast<long long>(i) * VE, x);
+    }
+}
+
+// WAVenc1d with the filter bank (transposed to [Cin*W][F]) and the input window staged in shared memory.
+// grid (ceil(Lc / 128), B); dynamic smem = (Cin*W*F + Cin*(128*S + W)) floats.
+template <typename T>
+__global__ void __launch_bounds__(256) cl_wavenc_smem_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ out,
+                                                             int Cin, int L, int Lc, int F, int W, int S, int pad) {
+    extern __shared__ float sm_enc[];
+    constexpr int TT = 128;
+    float* ws = sm_enc;                       // [Cin*W][F]
+    const int span = TT * S + W;
+    float* xs = ws + Cin * W * F;             // [Cin][span]
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    for (int i = threadIdx.x; i < Cin * W * F; i += blockDim.x) {
+        const int f = i % F, ck = i / F;      // w is [F][Cin][W]
+        ws[i] = w[static_cast<long long>(f) * Cin * W + ck];
+    }
+    for (int i = threadIdx.x; i < Cin * span; i += blockDim.x) {
+        const int c = i / span, j = i % span;
+        const int s = t0 * S - pad + j;
+        xs[i] = (s >= 0 && s < L) ? x[(static_cast<long long>(b) * Cin + c) * L + s] : 0.f;
+    }
+    __syncthreads();
+    const int rows = min(TT, Lc - t0);
+    for (int i = threadIdx.x; i < rows * F; i += blockDim.x) {
+        const int r = i / F, f = i % F;
+        float acc = 0.f;
+        for (int c = 0; c < Cin; ++c) {
+            const float* xr = xs + c * span + r * S;
+            const float* wr = ws + c * W * F + f;
+            for (int k = 0; k < W; ++k) acc = fmaf(wr[k * F], xr[k], acc);
+        }
+        cl_st<T>(out + (static_cast<long long>(b) * Lc + t0 + r) * F + f, acc);
+    }
+}
+
+// WAVdec1d for W == 2S (two (row, tap) pairs per output sample): filter bank [F][Cout][W] and the needed input rows
+// staged in shared memory. grid (ceil(L / TO), B), TO = 32 * S output samples per block.
+template <typename T>
+__global__ void __launch_bounds__(256) cl_wavdec_smem_kernel(const T* __restrict__ h, const float* __restrict__ w, float* __restrict__ y,
+                                                             int Lc, int L, int F, int Cout, int W, int S, int pad) {
+    extern __shared__ float sm_dec[];
+    const int TO = 32 * S;
+    const int nrows = 34;                     // rows i0-1 .. i0+32 cover every output of the tile
+    float* ws = sm_dec;                       // [F][Cout][W]
+    float* hs = ws + F * Cout * W;            // [nrows][F]
+    const int b = blockIdx.y, T0 = blockIdx.x * TO;
+    const int ibase = (T0 + pad) / S - 1;
+    for (int i = threadIdx.x; i < F * Cout * W; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < nrows * F; i += blockDim.x) {
+        const int r = ibase + i / F;
+        hs[i] = (r >= 0 && r < Lc) ? cl_ld<T>(h + (static_cast<long long>(b) * Lc + r) * F + i % F) : 0.f;
+    }
+    __syncthreads();
+    const int n = min(TO, L - T0);
+    for (int i = threadIdx.x; i < n * Cout; i += blockDim.x) {
+        const int c = i / n, tt = i % n;
+        const int u = T0 + tt + pad;
+        const int i0 = u / S - ibase, k0 = u % S;          // rows i0 (tap k0) and i0 - 1 (tap k0 + S)
+        const float* h0 = hs + i0 * F;
+        const float* h1 = h0 - F;
+        const float* w0 = ws + c * W + k0;
+        float acc = 0.f;
+        for (int f = 0; f < F; ++f) {
+            acc = fmaf(h0[f], w0[f * Cout * W], acc);
+            acc = fmaf(h1[f], w0[f * Cout * W + S], acc);
+        }
+        y[(static_cast<long long>(b) * Cout + c) * L + T0 + tt] = acc;
     }
 }
 

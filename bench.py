@@ -169,13 +169,110 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+UNET_CFG4 = dict(   # SURVEY.md §8(d) config 4 (BASELINE.json configs[3]): audio-diffusion-pytorch defaults
+    channels=128, cond_drop_prob=0.0, class_cond=False, text_cond=False, num_filters=128, window_length=32, stride=16,
+    in_channels=2, resnet_groups=8, kernel_multiplier_downsample=2, multipliers=[1, 2, 4, 4, 4, 4, 4],
+    factors=[4, 4, 4, 2, 2, 2], num_blocks=[2, 2, 2, 2, 2, 2], attentions=[False, False, False, True, True, True],
+    attention_heads=8, attention_multiplier=2, use_nearest_upsample=False, use_skip_scale=True,
+    use_attention_bottleneck=True)
+UNET_L, UNET_STEPS, UNET_FLOP_EVAL = 262144, 50, 61.69e9
+
+
+def run_unet(args, rank, world, local_rank):
+    """Secondary workload (BASELINE.json configs[3]): UNet1d with attention, 2 x 262144 stereo 48 kHz, EDM Heun 50 steps
+    (99 network evaluations per waveform). Same JSON contract; no roofline block (time is spread over ~400 launches per
+    evaluation, see profiles/)."""
+    import torch.distributed as dist
+    from audiodiffuser_b200 import EluDiffusion, EDMSampler, KarrasSchedule, UNet1dBase, _native
+    from audiodiffuser_b200.sharding import shard_noise
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or 8
+    torch.manual_seed(0)
+    net = UNet1dBase(precision=args.precision, **UNET_CFG4)
+    net.unet.to_out.to_out.weight.data.uniform_(-0.06, 0.06)          # zero-initialised in the reference (unet1d.py:619)
+    net = net.to(dev)
+    diff = EluDiffusion(sigma_data=SIGMA_DATA)
+    sampler = EDMSampler(s_tmin=0, s_tmax=float("inf"), s_churn=0.0, s_noise=1.0, num_steps=UNET_STEPS, cond_scale=1.0, use_heun=True)
+    sigmas = KarrasSchedule(0.002, 80.0, 7.0, UNET_STEPS)().to(dev)
+    noise_host = shard_noise(B * world, rank, world, UNET_L, base_seed=4321, channels=2).pin_memory()
+    noise_dev = noise_host.to(dev)
+    out_host = torch.empty_like(noise_host).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        return sampler(noise_dev, fn=diff.denoise_fn, net=net, sigmas=sigmas)
+
+    def step_e2e():
+        y = sampler(noise_host.to(dev, non_blocking=True), fn=diff.denoise_fn, net=net, sigmas=sigmas)
+        out_host.copy_(y, non_blocking=True)
+        return y
+
+    for _ in range(max(args.warmup, 1)):
+        y = step_resident()
+    _native.check_async()
+    assert torch.isfinite(y).all() and float(y.abs().max()) > 0
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    ms_res = timed(step_resident, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if clocks else None
+    _native.check_async()
+    if rank == 0:
+        nfe = 2 * UNET_STEPS - 1
+        total = B * world * args.steps
+        line = {"metric": "unet1d_stereo48k_edm_heun50_samples_per_sec", "value": total / (ms_res * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_res / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"UNet1d 102M (channels 128, multipliers 1-2-4-4-4-4-4, attention at the 3 deepest levels), "
+                                       f"2x{UNET_L} stereo 48 kHz, EDM Heun {UNET_STEPS} steps ({nfe} network evaluations), "
+                                       f"BASELINE.json configs[3]", "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": f"batch-sharded x{world}, no collective",
+                           "l2": "CUDA-graph replay of ~400 launches per evaluation; activations of the upper levels exceed L2"},
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": noise_host.numel() * 4,
+                        "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": None, "effective_tflops": UNET_FLOP_EVAL * nfe * total / (ms_res * 1e-3) / 1e12,
+                "ms_per_network_evaluation": ms_res / args.steps / nfe, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 8 UNet1d)")
+    ap.add_argument("--workload", default="diffwave", choices=["diffwave", "unet1d"],
+                    help="diffwave = the headline metric (BASELINE.json configs[1]); unet1d = configs[3]")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -183,6 +280,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "unet1d":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the headline DiffWave workload"}))
+            return
+        run_unet(args, rank, world, local_rank)
+        return
+    args.batch = args.batch or 256
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -190,15 +295,17 @@ def main():
     import torch.distributed as dist
     from audiodiffuser_b200 import EluDiffusion, EDMSampler, KarrasSchedule, WaveNetNoise, _native
     from audiodiffuser_b200.sharding import shard_noise
-    from oracle.weights import make_wavenet_state_dict
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    net = WaveNetNoise(C, LAYERS, CYCLE, precision=args.precision)
-    net.load_state_dict(make_wavenet_state_dict(C, LAYERS, seed=0), strict=True)
+    torch.manual_seed(0)
+    net = WaveNetNoise(C, LAYERS, CYCLE, precision=args.precision)      # the reference's own init scheme (wavenet.py:75, :30)
+    # the reference zero-initialises the output conv (wavenet.py:57-66): re-randomise it so the trajectory is not trivial
+    net.output_projection.conv.weight.data.normal_(0.0, 1.0 / 16.0)
+    net.output_projection.conv.bias.data.normal_(0.0, 0.05)
     net = net.to(dev)
     diff = EluDiffusion(sigma_data=SIGMA_DATA)
     sampler = EDMSampler(s_tmin=0, s_tmax=float("inf"), s_churn=0.0, s_noise=1.0, num_steps=STEPS_EDM, cond_scale=1.0,
