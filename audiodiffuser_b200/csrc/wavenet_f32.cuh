@@ -234,18 +234,23 @@ __global__ void __launch_bounds__(256) in_proj_kernel(const float* __restrict__ 
                                                       int scale_stride, const float* __restrict__ w_in,
                                                       const float* __restrict__ b_in, void* __restrict__ out, int B, int L,
                                                       int C) {
+    // thread -> fixed channel group g (its 8 weights / biases live in registers), rows strided; 32-bit index math only
     const int cg = C / 8;
-    const long long total = static_cast<long long>(B) * L * cg;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % cg);
-        const long long bt = i / cg;
-        const int b = static_cast<int>(bt / L);
+    const int g = threadIdx.x % cg;
+    const int rows_per_block = blockDim.x / cg;                  // C <= 2048: at least one row per block pass
+    if (static_cast<int>(threadIdx.x) >= rows_per_block * cg) return;
+    float wv[8], bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { wv[k] = w_in[g * 8 + k]; bv[k] = b_in[g * 8 + k]; }
+    const int total_rows = B * L;                                // < 2^31 (checked by the caller)
+    for (int bt = blockIdx.x * rows_per_block + threadIdx.x / cg; bt < total_rows; bt += gridDim.x * rows_per_block) {
+        const int b = bt / L;
         const float s = scale ? scale[b * scale_stride] : 1.0f;
         const float xv = __fmul_rn(s, x[bt]);
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(w_in[g * 8 + k], xv, b_in[g * 8 + k]), 0.f);
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(wv[k], xv, bv[k]), 0.f);
+        const long long i = static_cast<long long>(bt) * cg + g;
         if constexpr (BF16) {
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);

@@ -557,18 +557,23 @@ wavenet_tail_tc_kernel(const __grid_constant__ CUtensorMap tm_wsp, const TailTcP
         const int b = tile / p.tiles_per_b;
         const int t = (tile % p.tiles_per_b) * TC_TILE_T + row;
         const bool valid = t < p.L;
-        // ---- A operand: this thread converts 128 channels of its row (K-blocks 2 half, 2 half + 1)
+        // ---- A operand: warp w converts rows 16 w .. 16 w + 15; a warp-wide load covers one whole row (1 KB
+        //      contiguous), lane l owning channels 8 l .. 8 l + 7 = 16-byte chunk (l & 7) of K-block (l >> 3)
         {
-            const float4* src = reinterpret_cast<const float4*>(p.skip + (static_cast<long long>(b) * p.L + t) * TC_C + half * 128);
+            const int tile_t0 = (tile % p.tiles_per_b) * TC_TILE_T;
+            const float* src0 = p.skip + (static_cast<long long>(b) * p.L + tile_t0) * TC_C + lane * 8;
 #pragma unroll 4
-            for (int ch = 0; ch < 16; ++ch) {                 // 16 chunks of 8 channels
+            for (int i = 0; i < 16; ++i) {
+                const int r = warp * 16 + i;
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (valid) { v0 = src[2 * ch]; v1 = src[2 * ch + 1]; }
+                if (tile_t0 + r < p.L) {
+                    const float4* src = reinterpret_cast<const float4*>(src0 + static_cast<long long>(r) * TC_C);
+                    v0 = src[0]; v1 = src[1];
+                }
                 const uint4 o = make_uint4(pack_bf16x2(v0.x * p.scale, v0.y * p.scale), pack_bf16x2(v0.z * p.scale, v0.w * p.scale),
                                            pack_bf16x2(v1.x * p.scale, v1.y * p.scale), pack_bf16x2(v1.z * p.scale, v1.w * p.scale));
-                const int kb = 2 * half + (ch >> 3);
-                const int chunk = (ch & 7) ^ (row & 7);
-                *reinterpret_cast<uint4*>(smem + TailTcSmem::a + kb * TC_A_BYTES + row * 128 + chunk * 16) = o;
+                const int kb = lane >> 3, chunk = (lane & 7) ^ (r & 7);
+                *reinterpret_cast<uint4*>(smem + TailTcSmem::a + kb * TC_A_BYTES + r * 128 + chunk * 16) = o;
             }
         }
         fence_proxy_async_smem();

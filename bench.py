@@ -188,6 +188,7 @@ def run_unet(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or 8
     torch.manual_seed(0)
@@ -299,6 +300,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(0)
