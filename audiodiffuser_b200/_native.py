@@ -65,6 +65,13 @@ _SIGS = {
     "adb_cl_concat": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "adb_cl_wavenc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_cl_wavdec": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_wavenet_train_workspace_bytes": (c_int64, [c_void_p, c_int, c_int]),
+    "adb_wavenet_dsm_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p,
+                                              c_int64, c_void_p]),
+    "adb_wavenet_dsm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                         c_int64, c_void_p]),
+    "adb_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float,
+                               c_int, c_float, c_void_p]),
     "adb_wavenet_set_timing": (c_int, [c_void_p, c_int]),
     "adb_wavenet_timers": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
 }
@@ -117,6 +124,14 @@ def require_cuda_f32(t, name):
 
 def ptr(t):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def alloc_workspace(nbytes, device):
+    """uint8 scratch tensor plus a 1024-byte aligned pointer into it (TMA tiles need the alignment; the caching
+    allocator only guarantees 512)."""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    base = (buf.data_ptr() + 1023) // 1024 * 1024
+    return buf, c_void_p(base)
 
 
 _device_ok = set()

@@ -133,12 +133,14 @@ class WaveNetNoise(nn.Module):
             pass
 
     def _workspace(self, B, L, prec, device):
+        """(aligned pointer, byte count) of a cached scratch buffer large enough for (B, L, precision)."""
         need = N.lib().adb_wavenet_workspace_bytes(self._native(), B, L, prec)
         key = (device, prec)
-        ws = self._ws.get(key)
-        if ws is None or ws.numel() < need:
-            self._ws[key] = ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return ws, need
+        ent = self._ws.get(key)
+        if ent is None or ent[2] < need:
+            buf, p = N.alloc_workspace(need, device)
+            self._ws[key] = ent = (buf, p, need)
+        return ent[1], need
 
     def _prec(self):
         return N.PRECISIONS[self.precision]
@@ -161,7 +163,7 @@ class WaveNetNoise(nn.Module):
         ws, nbytes = self._workspace(B, L, prec, x.device)
         out = torch.empty(B, 1, L, dtype=torch.float32, device=x.device)
         N.check(N.lib().adb_wavenet_forward(h, N.ptr(x.contiguous()), N.ptr(t), N.ptr(None), 0, N.ptr(out), B, L, prec,
-                                            N.ptr(ws), nbytes, N.stream_ptr(x.device)))
+                                            ws, nbytes, N.stream_ptr(x.device)))
         return out
 
     @torch.no_grad()
@@ -178,7 +180,7 @@ class WaveNetNoise(nn.Module):
         dh = torch.zeros(dump_layers, B, L, C, dtype=torch.float32, device=x.device)
         ds = torch.zeros_like(dh)
         N.check(N.lib().adb_wavenet_forward_debug(h, N.ptr(x), N.ptr(t), N.ptr(None), 0, N.ptr(out), B, L, prec,
-                                                  N.ptr(ws), nbytes, N.ptr(dh), N.ptr(ds), dump_layers,
+                                                  ws, nbytes, N.ptr(dh), N.ptr(ds), dump_layers,
                                                   N.stream_ptr(x.device)))
         return out, dh, ds
 
@@ -192,7 +194,7 @@ class WaveNetNoise(nn.Module):
         ws, nbytes = self._workspace(B, L, prec, x.device)
         out = torch.empty_like(x)
         N.check(N.lib().adb_wavenet_denoise(h, N.ptr(x), N.ptr(sig), stride, sigma_data, N.ptr(out), B, L, prec,
-                                            N.ptr(ws), nbytes, N.stream_ptr(x.device)))
+                                            ws, nbytes, N.stream_ptr(x.device)))
         return out
 
     def _adb_fused_sample(self, noise, sig, num_steps, sigma_data, s_tmin, s_tmax, s_churn, s_noise, use_heun, alpha,
@@ -212,9 +214,18 @@ class WaveNetNoise(nn.Module):
                 raise N.AdbError(f"eps must have shape [num_steps, *noise.shape]; got {tuple(eps.shape)}")
         N.check(N.lib().adb_wavenet_sample_edm(h, N.ptr(noise), sig_arr, len(sig), num_steps, sigma_data, s_tmin, s_tmax,
                                                s_churn, s_noise, int(use_heun), alpha, N.ptr(eps), N.ptr(out), B, L,
-                                               prec, N.ptr(ws), nbytes, ctypes.byref(nfe),
+                                               prec, ws, nbytes, ctypes.byref(nfe),
                                                N.stream_ptr(noise.device)))
         return out, nfe.value
+
+    # ---- training step (fused DSM loss forward / backward; fp32 kernels) -----------------------------
+    def _adb_dsm_loss(self, x: Tensor, sigmas: Tensor, noise: Tensor, sigma_data: float) -> Tensor:
+        """loss [B] of Diffusion.forward (diffusion.py:65-97) as an autograd node whose backward runs the CUDA
+        backward pass and hands every parameter its gradient (so `loss.mean().backward(); optimizer.step()` and
+        DDP's gradient hooks work unchanged)."""
+        if x.ndim != 3 or x.shape[1] != 1:
+            raise N.AdbError(f"fused DiffWave training step expects x [B,1,L]; got {tuple(x.shape)}")
+        return _DsmLossFn.apply(x, sigmas, noise, float(sigma_data), self, *self.parameters())
 
     # ---- kernel-class timers (bench) ---------------------------------------------------------------
     def set_timing(self, enabled: bool):
@@ -225,6 +236,45 @@ class WaveNetNoise(nn.Module):
         cnt = (c_int64 * len(N.TIMER_NAMES))()
         N.check(N.lib().adb_wavenet_timers(self._native(), ms, cnt))
         return {n: (ms[i], cnt[i]) for i, n in enumerate(N.TIMER_NAMES)}
+
+
+class _DsmLossFn(torch.autograd.Function):
+    """Diffusion.forward through the fused backbone: forward = adb_wavenet_dsm_forward_train (activations kept in a
+    workspace tensor), backward = adb_wavenet_dsm_backward (flat gradient in state_dict order, split into views)."""
+
+    @staticmethod
+    def forward(ctx, x, sigmas, noise, sigma_data, net, *params):
+        lib = N.lib()
+        B, _, L = x.shape
+        h = net._native()
+        nbytes = lib.adb_wavenet_train_workspace_bytes(h, B, L)
+        ws_buf, ws = N.alloc_workspace(nbytes, x.device)
+        loss = torch.empty(B, dtype=torch.float32, device=x.device)
+        N.check(lib.adb_wavenet_dsm_forward_train(h, N.ptr(x), N.ptr(noise), N.ptr(sigmas), sigma_data, N.ptr(loss), B, L,
+                                                  ws, nbytes, N.stream_ptr(x.device)))
+        ctx.net, ctx.ws, ctx.ws_buf, ctx.nbytes, ctx.sigma_data = net, ws, ws_buf, nbytes, sigma_data
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.save_for_backward(x, sigmas)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        x, sigmas = ctx.saved_tensors
+        lib, net = N.lib(), ctx.net
+        B, _, L = x.shape
+        n_params = sum(math.prod(s) for s in ctx.shapes)
+        flat = torch.empty(n_params, dtype=torch.float32, device=x.device)
+        up = N.require_cuda_f32(grad_loss, "grad_loss").reshape(B)
+        N.check(lib.adb_wavenet_dsm_backward(net._native(), N.ptr(x), N.ptr(sigmas), ctx.sigma_data, N.ptr(up), N.ptr(flat), B, L,
+                                             ctx.ws, ctx.nbytes, N.stream_ptr(x.device)))
+        ctx.ws = ctx.ws_buf = None
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = math.prod(shp)
+            grads.append(flat[off:off + n].view(shp))
+            off += n
+        net._last_flat_grad = flat
+        return (None, None, None, None, None, *grads)
 
 
 class EDMDenoiser(nn.Module):

@@ -113,7 +113,8 @@ class EluDiffusion(Diffusion):
 
         `noise` (optional, same shape as x) replaces the internal `torch.randn_like(x)`
         (diffusion.py:76) so tests can fix it; by default it is drawn exactly like the reference.
-        Forward value only (evaluation / validation loss); see DESIGN.md for the training-step status.
+        With gradients enabled and the fused `WaveNetNoise` as `net`, the returned loss carries an autograd node
+        whose backward runs the CUDA backward pass (training step); otherwise only the value is computed.
         """
         x = N.require_cuda_f32(x, "x")
         N.ensure_device(x.device)
@@ -126,6 +127,10 @@ class EluDiffusion(Diffusion):
             noise = torch.randn_like(x)
         noise = N.require_cuda_f32(noise, "noise")
         sig, _ = to_batch(B, x.device, xs=sigmas)
+        fused_train = getattr(net, "_adb_dsm_loss", None)
+        if fused_train is not None and torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+            # training step: loss with an autograd node whose backward is the CUDA backward pass
+            return fused_train(x, sig.contiguous(), noise, float(self.sigma_data))
         lib, st = N.lib(), N.stream_ptr(x.device)
         x_noisy = torch.empty_like(x)
         net_in = torch.empty_like(x)

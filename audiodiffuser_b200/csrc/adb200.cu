@@ -21,6 +21,7 @@
 #include "wavenet_tc2.cuh"
 #include "cl_ops.cuh"
 #include "cl_conv_tc.cuh"
+#include "train_kernels.cuh"
 
 using namespace adb;
 
@@ -241,6 +242,8 @@ struct LayerW {
     const float *v1, *g1, *b1, *wp, *bp, *v2, *g2, *b2;
     // folded fp32 (owned)
     float *w1f, *w2f;
+    // transposed / tap-reversed copies for the data-gradient convolutions (training step)
+    float *w2T, *w1d;
 };
 
 struct TimerPair {
@@ -262,6 +265,8 @@ struct adb_wavenet {
     const float *v_in, *g_in, *b_in, *fc1w, *fc1b, *fc2w, *fc2b, *v_sp, *g_sp, *b_sp, *w_out, *b_out;
     float* w_in_f = nullptr;          // folded [C]
     float* wsp_f = nullptr;           // folded [C][C] (ci, co)
+    float* wspT = nullptr;            // [co][ci] (training step)
+    float* d_scale = nullptr;         // g / ||v|| per weight-normed conv: [0] input, [1 + 2l] dilated, [2 + 2l] output, [last] skip
     const float** d_wp = nullptr;     // device arrays of per-layer pointers
     const float** d_bp = nullptr;
     // tensor-core path (C == 256 only)
@@ -478,7 +483,8 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     WnJob* d_jobs = nullptr;
     float* d_scale = nullptr;
     CKN(cudaMalloc(&d_jobs, sizeof(WnJob) * njobs));
-    CKN(cudaMalloc(&d_scale, sizeof(float) * njobs));
+    CKN(dmalloc(n, &d_scale, njobs));
+    n->d_scale = d_scale;
     CKN(cudaMemcpy(d_jobs, jobs.data(), sizeof(WnJob) * njobs, cudaMemcpyHostToDevice));
     wn_scale_kernel<<<njobs, 256>>>(d_jobs, d_scale);
     CKN(cudaGetLastError());
@@ -496,7 +502,15 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         pack_conv_f32_kernel<<<grid_for(6LL * C * C), 256>>>(w.v1, d_scale + 1 + 2 * l, w.w1f, 2 * C, C, 3);
         pack_conv_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.v2, d_scale + 2 + 2 * l, w.w2f, 2 * C, C, 1);
         h_wp[l] = w.wp; h_bp[l] = w.bp;
+        CKN(dmalloc(n, &w.w2T, 2ULL * C * C));
+        CKN(dmalloc(n, &w.w1d, 3ULL * 2 * C * C));
+        transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2f, w.w2T, C, 2 * C);                 // [ci][co] -> [co][ci]
+        for (int tap = 0; tap < 3; ++tap)                                                              // tap-reversed transpose
+            transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w1f + static_cast<size_t>(2 - tap) * C * 2 * C,
+                                                                 w.w1d + static_cast<size_t>(tap) * 2 * C * C, C, 2 * C);
     }
+    CKN(dmalloc(n, &n->wspT, static_cast<size_t>(C) * C));
+    transpose_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wsp_f, n->wspT, C, C);
     CKN(cudaGetLastError());
     CKN(dmalloc(n, &n->d_wp, layers));
     CKN(dmalloc(n, &n->d_bp, layers));
@@ -547,7 +561,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             const char* pe = getenv("ADB_TC_PAIR");
             if (pe) n->pair = atoi(pe) != 0;
         }
-        if (rc2) { adb_wavenet_destroy(n); cudaFree(d_jobs); cudaFree(d_scale); return rc2; }
+        if (rc2) { adb_wavenet_destroy(n); cudaFree(d_jobs); return rc2; }
         CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
@@ -555,7 +569,6 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     }
     CKN(cudaDeviceSynchronize());
     cudaFree(d_jobs);
-    cudaFree(d_scale);
 #undef CKN
     *out = n;
     return ADB_OK;
@@ -964,3 +977,4 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
 }
 
 #include "cl_api.inc"
+#include "train.inc"

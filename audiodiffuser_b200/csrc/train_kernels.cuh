@@ -1,0 +1,359 @@
+// Backward-pass kernels of the DiffWave training step (fp32 CUDA-core path).
+//
+// Reference: the autograd graph of Diffusion.forward (src/models/components/diffusion.py:65-97) through
+// WaveNetNoise (src/models/backbones/wavenet.py:94-180) as built by PyTorch; the forward arithmetic is the one of
+// wavenet_f32.cuh. Every data-gradient GEMM reuses conv_cl_f32 (a transposed / tap-reversed convolution is again a
+// channels-last convolution); this file adds the weight-gradient GEMM (reduction over batch x time), the element-wise
+// derivative kernels, the bias / embedding reductions, the weight-norm chain rule and the fused AdamW update
+// (torch.optim.AdamW semantics, configs/model/diffunet_complex.yaml:7-12).
+#pragma once
+#include "ptx.cuh"
+
+namespace adb {
+
+// out[b][t][c] = h[b][t][c] + p[b][c]   (wavenet.py:108-109, materialised for the weight gradient)
+__global__ void __launch_bounds__(256) add_bcast_kernel(const float* __restrict__ h, const float* __restrict__ p,
+                                                        float* __restrict__ out, int B, int L, int C) {
+    const long long total4 = static_cast<long long>(B) * L * C / 4;
+    const int c4n = C / 4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c4 = static_cast<int>(i % c4n);
+        const int b = static_cast<int>(i / (static_cast<long long>(L) * c4n));
+        float4 v = reinterpret_cast<const float4*>(h)[i];
+        const float4 e = reinterpret_cast<const float4*>(p + static_cast<long long>(b) * C)[c4];
+        v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+// z = sigmoid(g) tanh(f)  =>  dg = dz tanh(f) s (1 - s),  df = dz s (1 - tanh(f)^2)   (wavenet.py:111-112)
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dz,
+                                                       float* __restrict__ dy, long long rows, int C) {
+    const long long total = rows * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / C;
+        const int c = static_cast<int>(i % C);
+        const float g = y[r * 2 * C + c], f = y[r * 2 * C + C + c];
+        const float s = 1.0f / (1.0f + expf(-g)), th = tanhf(f), d = dz[i];
+        dy[r * 2 * C + c] = d * th * s * (1.0f - s);
+        dy[r * 2 * C + C + c] = d * s * (1.0f - th * th);
+    }
+}
+
+// do[r][0:C] = dh_out[r] / sqrt(2) (0 if dh_out == nullptr: the last block's residual output is unused) ; do[r][C:2C] = dskip[r]
+// (wavenet.py:114-115, :149)
+__global__ void __launch_bounds__(256) build_do_kernel(const float* __restrict__ dh_out, const float* __restrict__ dskip,
+                                                       float* __restrict__ dout, long long rows, int C) {
+    const long long total = rows * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / C;
+        const int c = static_cast<int>(i % C);
+        dout[r * 2 * C + c] = dh_out ? dh_out[i] * 0.70710678118654752f : 0.f;
+        dout[r * 2 * C + C + c] = dskip[i];
+    }
+}
+
+// out = a * x + b * y (y may be nullptr)
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float b,
+                                                    float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = y ? fmaf(a, x[i], b * y[i]) : a * x[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: out[i][j] += sum_{b, t : 0 <= t + shift < L} A[b][t + shift][i] * G[b][t][j]
+// (A: [nb][L][Ca] layer input, G: [nb][L][Cb] output gradient). Tile 64 x 64 outputs, each block reduces a slab of
+// `rows_per_block` time steps of one sample and adds its partial tile with fp32 atomics. out row pitch = ldo.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wgrad_f32_kernel(const float* __restrict__ A, const float* __restrict__ G,
+                                                        float* __restrict__ out, int L, int Ca, int Cb, int shift, long long ldo,
+                                                        int rows_per_block, float a_scale) {
+    constexpr int BK = 16;
+    __shared__ float As[BK][64 + 4];
+    __shared__ float Gs[BK][64];
+    const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    const int slabs = (L + rows_per_block - 1) / rows_per_block;
+    const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
+    const int t_lo = slab * rows_per_block, t_hi = min(L, t_lo + rows_per_block);
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const float* Ab = A + static_cast<long long>(b) * L * Ca;
+    const float* Gb = G + static_cast<long long>(b) * L * Cb;
+    float acc[4][4] = {};
+    const int l_row = tid / 16, l_c = (tid % 16) * 4;           // 16 rows x 64 channels per load pass
+    for (int t = t_lo; t < t_hi; t += BK) {
+        {
+            const int tt = t + l_row, s = tt + shift;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vg = va;
+            if (tt < t_hi) {
+                vg = *reinterpret_cast<const float4*>(Gb + static_cast<long long>(tt) * Cb + j0 + l_c);
+                if (s >= 0 && s < L) va = *reinterpret_cast<const float4*>(Ab + static_cast<long long>(s) * Ca + i0 + l_c);
+            }
+            *reinterpret_cast<float4*>(&As[l_row][l_c]) = va;
+            *reinterpret_cast<float4*>(&Gs[l_row][l_c]) = vg;
+        }
+        __syncthreads();
+        float part[4][4] = {};
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 g = *reinterpret_cast<const float4*>(&Gs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], gv[j], part[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            atomicAdd(out + static_cast<long long>(i0 + ty * 4 + i) * ldo + j0 + tx * 4 + j, acc[i][j] * a_scale);
+}
+
+// Column sums: out[(per_sample ? b : 0)][c] += sum_t in[b][t][c]. grid (chunks, nb), 256 threads, C % 4 == 0, C <= 1024.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, float* __restrict__ out, int L, int C,
+                                                     int chunks, int per_sample) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int rows_per = (L + chunks - 1) / chunks;
+    const int r0 = chunk * rows_per, r1 = min(L, r0 + rows_per);
+    __shared__ float red[1024];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) red[c] = 0.f;
+    __syncthreads();
+    const int c4n = C / 4;
+    const int rstep = max(1, 256 / c4n), rofs = threadIdx.x / c4n;
+    if (rofs < rstep) {
+        for (int c4 = threadIdx.x % c4n; c4 < c4n; c4 += 256) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = r0 + rofs; r < r1; r += rstep) {
+                const float4 v = *reinterpret_cast<const float4*>(in + (static_cast<long long>(b) * L + r) * C + c4 * 4);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            atomicAdd(&red[c4 * 4], s.x); atomicAdd(&red[c4 * 4 + 1], s.y);
+            atomicAdd(&red[c4 * 4 + 2], s.z); atomicAdd(&red[c4 * 4 + 3], s.w);
+        }
+    }
+    __syncthreads();
+    float* o = out + (per_sample ? static_cast<long long>(b) * C : 0);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(o + c, red[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail backward (wavenet.py:177-179): F = b_out + sum_c w_out[c] s2[c], s2 = relu(...)
+//   ds2[r][c] = dF[r] w_out[c] [s2 > 0] ; dw_out[c] += sum_r dF[r] s2[r][c] ; db_out += sum_r dF[r]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__ dF, const float* __restrict__ s2,
+                                                       const float* __restrict__ w_out, float* __restrict__ ds2,
+                                                       float* __restrict__ dw_out, float* __restrict__ db_out, long long rows,
+                                                       int C) {
+    __shared__ float acc_w[1024];
+    __shared__ float acc_b;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) acc_w[c] = 0.f;
+    if (threadIdx.x == 0) acc_b = 0.f;
+    __syncthreads();
+    const int c = threadIdx.x % C;                  // C <= 256 here: fixed channel per thread
+    const int rstep = blockDim.x / C, rofs = threadIdx.x / C;
+    float lw = 0.f, lb = 0.f;
+    const float wc = w_out[c];
+    for (long long r = static_cast<long long>(blockIdx.x) * rstep + rofs; r < rows; r += static_cast<long long>(gridDim.x) * rstep) {
+        const float g = dF[r], s = s2[r * C + c];
+        ds2[r * C + c] = s > 0.f ? g * wc : 0.f;
+        lw = fmaf(g, s, lw);
+        if (c == 0) lb += g;
+    }
+    atomicAdd(&acc_w[c], lw);
+    if (c == 0) atomicAdd(&acc_b, lb);
+    __syncthreads();
+    for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(dw_out + k, acc_w[k]);
+    if (threadIdx.x == 0) atomicAdd(db_out, acc_b);
+}
+
+// Input projection backward (wavenet.py:172-174): h0 = relu(w_in x~ + b_in):
+//   dw_in[c] += sum_r [h0 > 0] dh0[r][c] x~[r] ; db_in[c] += sum_r [h0 > 0] dh0[r][c] ; x~[r] = scale_b x[r]
+__global__ void __launch_bounds__(256) inproj_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ h0,
+                                                         const float* __restrict__ x, const float* __restrict__ scale,
+                                                         float* __restrict__ dw_in, float* __restrict__ db_in, int L,
+                                                         long long rows, int C) {
+    __shared__ float aw[1024], ab[1024];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { aw[c] = 0.f; ab[c] = 0.f; }
+    __syncthreads();
+    const int c = threadIdx.x % C;
+    const int rstep = blockDim.x / C, rofs = threadIdx.x / C;
+    float lw = 0.f, lb = 0.f;
+    for (long long r = static_cast<long long>(blockIdx.x) * rstep + rofs; r < rows; r += static_cast<long long>(gridDim.x) * rstep) {
+        const float m = h0[r * C + c] > 0.f ? dh0[r * C + c] : 0.f;
+        const float xv = __fmul_rn(scale[r / L], x[r]);
+        lw = fmaf(m, xv, lw);
+        lb += m;
+    }
+    atomicAdd(&aw[c], lw);
+    atomicAdd(&ab[c], lb);
+    __syncthreads();
+    for (int k = threadIdx.x; k < C; k += blockDim.x) { atomicAdd(dw_in + k, aw[k]); atomicAdd(db_in + k, ab[k]); }
+}
+
+// Loss backward (diffusion.py:60-63, :92-95): loss_b = lambda_b / n * sum_i (D_i - x_i)^2, D = clamp(c_skip xn + c_out F)
+//   dF_i = upstream * (2 lambda_b / n) (D_i - x_i) c_out [-1 <= c_skip xn + c_out F <= 1]
+__global__ void __launch_bounds__(256) dsm_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x_noisy,
+                                                           const float* __restrict__ F, const float* __restrict__ sigmas,
+                                                           float sigma_data, float sd2, float upstream, float* __restrict__ dF,
+                                                           int B, long long n_per) {
+    const long long total = static_cast<long long>(B) * n_per;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i / n_per);
+        const float sg = sigmas[b];
+        const PrecondCoef c = precond_coef(sg, sigma_data, sd2);
+        const float pre = __fadd_rn(__fmul_rn(c.c_skip, x_noisy[i]), __fmul_rn(c.c_out, F[i]));
+        const float D = clamp1(pre);
+        const float lam = (sg * sg + sd2) / ((sg * sigma_data) * (sg * sigma_data));
+        const bool pass = pre >= -1.0f && pre <= 1.0f;           // torch.clamp passes the gradient on the closed interval
+        dF[i] = pass ? upstream * 2.0f * lam / static_cast<float>(n_per) * (D - x[i]) * c.c_out : 0.f;
+    }
+}
+
+// Per-layer step-embedding projection backward (wavenet.py:108): p = Wp emb + bp, given dp [B][C]:
+//   dWp[c][k] += sum_b dp[b][c] emb[b][k] ; dbp[c] += sum_b dp[b][c] ; demb[b][k] += sum_c dp[b][c] Wp[c][k]
+// grid (layers), 512 threads (k), small B.
+__global__ void __launch_bounds__(512) embproj_bwd_kernel(const float* __restrict__ dp /*[layers][B][C]*/, const float* __restrict__ emb,
+                                                          const float* const* __restrict__ wp, float* __restrict__ grad_layers,
+                                                          long long layer_stride, long long wp_off, long long bp_off,
+                                                          float* __restrict__ demb, int B, int C) {
+    const int layer = blockIdx.x, k = threadIdx.x;
+    const float* dpl = dp + static_cast<long long>(layer) * B * C;
+    const float* w = wp[layer];
+    float* dw = grad_layers + layer * layer_stride + wp_off;      // this block owns the layer's dWp / dbp: plain stores
+    float* db = grad_layers + layer * layer_stride + bp_off;
+    for (int c = 0; c < C; ++c) {
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc = fmaf(dpl[b * C + c], emb[b * 512 + k], acc);
+        dw[static_cast<long long>(c) * 512 + k] = acc;
+    }
+    for (int c = k; c < C; c += 512) {
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += dpl[b * C + c];
+        db[c] = acc;
+    }
+    for (int b = 0; b < B; ++b) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc = fmaf(dpl[b * C + c], w[static_cast<long long>(c) * 512 + k], acc);
+        atomicAdd(demb + b * 512 + k, acc);
+    }
+}
+
+// dF[r] *= upstream[r / L]   (per-sample weights of the upstream gradient)
+__global__ void __launch_bounds__(256) scale_rows_kernel(float* __restrict__ v, const float* __restrict__ w, long long n, int L) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        v[i] *= w[i / L];
+}
+
+// Step-embedding MLP backward (wavenet.py:88-92, :139-141): recomputes the forward of one sample, then
+//   d_a2 = demb swish'(a2) ; dfc2 += d_a2 e1^T ; d_e1 = fc2^T d_a2 ; d_a1 = d_e1 swish'(a1) ; dfc1 += d_a1 e0^T
+// one block of 512 threads per sample; weight gradients accumulate with atomics over samples.
+__device__ __forceinline__ float swish_grad(float a) {
+    const float s = 1.0f / (1.0f + expf(-a));
+    return s * (1.0f + a * (1.0f - s));
+}
+__global__ void __launch_bounds__(512) embed_mlp_bwd_kernel(const float* __restrict__ c_noise, const float* __restrict__ w1,
+                                                            const float* __restrict__ b1, const float* __restrict__ w2,
+                                                            const float* __restrict__ b2, const float* __restrict__ demb,
+                                                            float* __restrict__ dw1, float* __restrict__ db1,
+                                                            float* __restrict__ dw2, float* __restrict__ db2) {
+    __shared__ float e0[128], e1[512], da2[512], de1[512];
+    const int b = blockIdx.x, j = threadIdx.x;
+    const float t = c_noise[b];
+    if (j < 128) {
+        const int jj = j % 64;
+        const float arg = t * expf(-static_cast<float>(jj) * 4.0f / 63.0f);
+        e0[j] = (j < 64) ? sinf(arg) : cosf(arg);
+    }
+    __syncthreads();
+    float a1 = b1[j];
+    for (int k = 0; k < 128; ++k) a1 = fmaf(w1[j * 128 + k], e0[k], a1);
+    e1[j] = a1 / (1.0f + expf(-a1));
+    __syncthreads();
+    float a2 = b2[j];
+    for (int k = 0; k < 512; ++k) a2 = fmaf(w2[j * 512 + k], e1[k], a2);
+    const float d2 = demb[b * 512 + j] * swish_grad(a2);
+    da2[j] = d2;
+    atomicAdd(db2 + j, d2);
+    __syncthreads();
+    for (int k = 0; k < 512; ++k) atomicAdd(dw2 + j * 512 + k, d2 * e1[k]);
+    float acc = 0.f;
+    for (int jj = 0; jj < 512; ++jj) acc = fmaf(w2[jj * 512 + j], da2[jj], acc);      // d_e1[j] = sum_jj fc2[jj][j] d_a2[jj]
+    const float d1 = acc * swish_grad(a1);
+    de1[j] = d1;
+    atomicAdd(db1 + j, d1);
+    for (int k = 0; k < 128; ++k) atomicAdd(dw1 + j * 128 + k, d1 * e0[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight-norm chain rule (wavenet.py:44-51, scalar g): w = v g / ||v||, given dW in the packed layout
+// [taps][Cin][Cout] (what wgrad produces) and v in torch layout [Cout][Cin][taps]:
+//   dot = sum dW v ; dg = dot / ||v|| ; dv = (g / ||v||) (dW - v dot / ||v||^2)
+// pass 1 (many blocks): dot via atomics ; pass 2: element-wise, writing dv in torch layout.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wn_bwd_dot_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                         float* __restrict__ dot, int Cout, int Cin, int taps) {
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    float acc = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        const int ci = static_cast<int>((i / Cout) % Cin);
+        const int tap = static_cast<int>(i / (static_cast<long long>(Cout) * Cin));
+        acc = fmaf(dw[i], v[(static_cast<long long>(co) * Cin + ci) * taps + tap], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dot, acc);
+}
+__global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                           const float* __restrict__ g, const float* __restrict__ scale,
+                                                           const float* __restrict__ dot, float* __restrict__ dv,
+                                                           float* __restrict__ dg, int Cout, int Cin, int taps) {
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    const float s = scale[0];                       // g / ||v||
+    const float nrm = g[0] / s;                     // ||v||
+    const float d = dot[0];
+    const float k = d / (nrm * nrm);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        const int ci = static_cast<int>((i / Cout) % Cin);
+        const int tap = static_cast<int>(i / (static_cast<long long>(Cout) * Cin));
+        const long long j = (static_cast<long long>(co) * Cin + ci) * taps + tap;
+        dv[j] = s * (dw[i] - v[j] * k);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) dg[0] = d / nrm;
+}
+
+// torch.optim.AdamW step on flat vectors (decoupled weight decay; bias-corrected moments):
+//   p *= 1 - lr wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr, float beta1, float beta2,
+                                                    float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        float pi = p[i] * (1.0f - lr * wd);
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi -= (lr / bc1) * (mi / denom);
+        p[i] = pi;
+    }
+}
+
+}  // namespace adb
