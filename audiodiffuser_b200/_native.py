@@ -41,6 +41,7 @@ _SIGS = {
     "adb_edm_dsm_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int64, c_void_p]),
     "adb_wavenet_param_count": (c_int64, [c_int, c_int]),
     "adb_wavenet_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int64, c_int]),
+    "adb_wavenet_load_params": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
     "adb_wavenet_destroy": (None, [c_void_p]),
     "adb_wavenet_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int]),
     "adb_wavenet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,

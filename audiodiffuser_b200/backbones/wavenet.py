@@ -91,6 +91,7 @@ class WaveNetNoise(nn.Module):
         self.output_projection = _ZeroConv(residual_channels, 1)
         self._handle = None
         self._handle_key = None
+        self._handle_dev = None
         self._ws = {}
 
     # ---- native handle management ----------------------------------------------------------------
@@ -108,18 +109,30 @@ class WaveNetNoise(nn.Module):
         N.ensure_device(dev)
         key = self._param_key()
         if self._handle is None or key != self._handle_key:
-            self._free()
             flat = self.flat_parameters().contiguous()
             lib = N.lib()
             expect = lib.adb_wavenet_param_count(self.residual_channels, self.residual_layers)
             if flat.numel() != expect:
                 raise N.AdbError(f"flat parameter vector has {flat.numel()} values, library expects {expect}")
-            h = c_void_p()
             with torch.cuda.device(dev):
-                N.check(lib.adb_wavenet_create(ctypes.byref(h), self.residual_channels, self.residual_layers,
-                                               self.dilation_cycle, N.ptr(flat), flat.numel(), 1))
-            self._handle, self._handle_key = h, key
+                if self._handle is not None and self._handle_dev == dev:
+                    # same configuration, new values (optimizer step / load_state_dict): refresh in place
+                    torch.cuda.current_stream(dev).synchronize()
+                    N.check(lib.adb_wavenet_load_params(self._handle, N.ptr(flat), flat.numel(), 1))
+                    torch.cuda.synchronize(dev)
+                else:
+                    self._free()
+                    h = c_void_p()
+                    N.check(lib.adb_wavenet_create(ctypes.byref(h), self.residual_channels, self.residual_layers,
+                                                   self.dilation_cycle, N.ptr(flat), flat.numel(), 1))
+                    self._handle, self._handle_dev = h, dev
+            self._handle_key = key
         return self._handle
+
+    def parameters_updated(self):
+        """Tell the module its parameters were changed outside torch's version tracking (a fused optimizer step on
+        the flat vector): the packed device weights are rebuilt on the next call."""
+        self._handle_key = None
 
     def _free(self):
         if self._handle is not None:

@@ -267,6 +267,9 @@ struct adb_wavenet {
     float* wsp_f = nullptr;           // folded [C][C] (ci, co)
     float* wspT = nullptr;            // [co][ci] (training step)
     float* d_scale = nullptr;         // g / ||v|| per weight-normed conv: [0] input, [1 + 2l] dilated, [2 + 2l] output, [last] skip
+    WnJob* d_jobs = nullptr;
+    float* wpT = nullptr;             // [512][C] scratch of refold
+    std::vector<int64_t> counts, dst_off;   // flat-vector pieces (state_dict order) and their offsets in `params`
     const float** d_wp = nullptr;     // device arrays of per-layer pointers
     const float** d_bp = nullptr;
     // tensor-core path (C == 256 only)
@@ -405,6 +408,52 @@ extern "C" void adb_wavenet_destroy(adb_wavenet* net) {
     delete net;
 }
 
+// Everything derived from the parameters: weight-norm scales, folded fp32 weights (+ transposed copies for the
+// backward), tensor-core packing and the step-embedding fold tables. Kernels only, legacy default stream.
+static int refold(adb_wavenet* n) {
+    const int C = n->C, layers = n->layers, njobs = 2 * layers + 2;
+    wn_scale_kernel<<<njobs, 256>>>(n->d_jobs, n->d_scale);
+    scale_copy_kernel<<<1, 256>>>(n->v_in, n->d_scale + 0, n->w_in_f, C);
+    pack_conv_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->v_sp, n->d_scale + njobs - 1, n->wsp_f, C, C, 1);
+    transpose_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wsp_f, n->wspT, C, C);
+    for (int l = 0; l < layers; ++l) {
+        LayerW& w = n->L[l];
+        pack_conv_f32_kernel<<<grid_for(6LL * C * C), 256>>>(w.v1, n->d_scale + 1 + 2 * l, w.w1f, 2 * C, C, 3);
+        pack_conv_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.v2, n->d_scale + 2 + 2 * l, w.w2f, 2 * C, C, 1);
+        transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2f, w.w2T, C, 2 * C);                 // [ci][co] -> [co][ci]
+        for (int tap = 0; tap < 3; ++tap)                                                              // tap-reversed transpose
+            transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w1f + static_cast<size_t>(2 - tap) * C * 2 * C,
+                                                                 w.w1d + static_cast<size_t>(tap) * 2 * C * C, C, 2 * C);
+    }
+    CK(cudaGetLastError());
+    n->tc_ready = false;
+    if (C == TC_C) {
+        const long long ldm = static_cast<long long>(layers) * 1536;
+        for (int l = 0; l < layers; ++l) {
+            LayerW& w = n->L[l];
+            pack_tc_layer_kernel<<<148 * 4, 256>>>(w.w1f, w.w2f, n->wtc + static_cast<size_t>(l) * 32 * 256 * 64);
+            transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, n->wpT, C, 512);     // [C][512] -> [512][C] (stream-ordered reuse)
+            for (int tap = 0; tap < 3; ++tap) {
+                ConvF32Args a;
+                memset(&a, 0, sizeof a);
+                // mtab[k][l,tap,co] = sum_ci Wp[ci][k] * W1[tap][ci][co]
+                a.in = n->wpT; a.w = w.w1f + static_cast<size_t>(tap) * C * 2 * C; a.out = n->mtab + (l * 3 + tap) * 512;
+                a.nb = 1; a.L = 512; a.Cin = C; a.Cout = 2 * C; a.taps = 1; a.dil = 1;
+                a.ldw = 2 * C; a.ldo = ldm; a.in_scale = 1.f;
+                CK(conv_cl_f32(a, 0));
+                // cvec[l,tap,co] = sum_ci bp[ci] * W1[tap][ci][co] (+ b1[co] for the centre tap)
+                a.in = w.bp; a.out = n->cvec + (l * 3 + tap) * 512; a.L = 1; a.ldo = 2 * C;
+                a.bias = (tap == 1) ? w.b1 : nullptr;
+                CK(conv_cl_f32(a, 0));
+            }
+        }
+        pack_tc_tail_kernel<<<64, 256>>>(n->wsp_f, n->wsp_tc);
+        CK(cudaGetLastError());
+        n->tc_ready = true;
+    }
+    return ADB_OK;
+}
+
 extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycle, const float* params, int64_t n_params,
                                   int on_device) {
     REQUIRE(out && params, "adb_wavenet_create: null argument");
@@ -442,6 +491,8 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         src_total += counts[i];
     }
     if (src_total != n_params) { adb_wavenet_destroy(n); return fail(ADB_ERR_INVALID, "internal: parameter carve mismatch"); }
+    n->counts = counts;
+    n->dst_off = dst_off;
     CKN(dmalloc(n, &n->params, static_cast<size_t>(padded)));
     CKN(cudaMemset(n->params, 0, sizeof(float) * padded));
     {
@@ -471,7 +522,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     n->b_sp = take(C); n->g_sp = take(1); n->v_sp = take(static_cast<int64_t>(C) * C);
     n->w_out = take(C); n->b_out = take(1);
 
-    // ---- weight-norm scales: one block per weight-normed conv ----
+    // ---- buffers derived from the parameters (filled by refold) ----
     const int njobs = 2 * layers + 2;
     std::vector<WnJob> jobs(njobs);
     jobs[0] = {n->v_in, n->g_in, C};
@@ -480,76 +531,32 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         jobs[2 + 2 * l] = {n->L[l].v2, n->L[l].g2, 2LL * C * C};
     }
     jobs[njobs - 1] = {n->v_sp, n->g_sp, static_cast<long long>(C) * C};
-    WnJob* d_jobs = nullptr;
-    float* d_scale = nullptr;
-    CKN(cudaMalloc(&d_jobs, sizeof(WnJob) * njobs));
-    CKN(dmalloc(n, &d_scale, njobs));
-    n->d_scale = d_scale;
-    CKN(cudaMemcpy(d_jobs, jobs.data(), sizeof(WnJob) * njobs, cudaMemcpyHostToDevice));
-    wn_scale_kernel<<<njobs, 256>>>(d_jobs, d_scale);
-    CKN(cudaGetLastError());
-
-    // ---- folded fp32 weights ----
+    CKN(dmalloc(n, &n->d_jobs, njobs));
+    CKN(dmalloc(n, &n->d_scale, njobs));
+    CKN(cudaMemcpy(n->d_jobs, jobs.data(), sizeof(WnJob) * njobs, cudaMemcpyHostToDevice));
     CKN(dmalloc(n, &n->w_in_f, C));
-    scale_copy_kernel<<<1, 256>>>(n->v_in, d_scale + 0, n->w_in_f, C);
     CKN(dmalloc(n, &n->wsp_f, static_cast<size_t>(C) * C));
-    pack_conv_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->v_sp, d_scale + njobs - 1, n->wsp_f, C, C, 1);
+    CKN(dmalloc(n, &n->wspT, static_cast<size_t>(C) * C));
+    CKN(dmalloc(n, &n->wpT, 512ULL * C));
     std::vector<const float*> h_wp(layers), h_bp(layers);
     for (int l = 0; l < layers; ++l) {
         LayerW& w = n->L[l];
         CKN(dmalloc(n, &w.w1f, 3ULL * C * 2 * C));
         CKN(dmalloc(n, &w.w2f, 2ULL * C * C));
-        pack_conv_f32_kernel<<<grid_for(6LL * C * C), 256>>>(w.v1, d_scale + 1 + 2 * l, w.w1f, 2 * C, C, 3);
-        pack_conv_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.v2, d_scale + 2 + 2 * l, w.w2f, 2 * C, C, 1);
-        h_wp[l] = w.wp; h_bp[l] = w.bp;
         CKN(dmalloc(n, &w.w2T, 2ULL * C * C));
         CKN(dmalloc(n, &w.w1d, 3ULL * 2 * C * C));
-        transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2f, w.w2T, C, 2 * C);                 // [ci][co] -> [co][ci]
-        for (int tap = 0; tap < 3; ++tap)                                                              // tap-reversed transpose
-            transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w1f + static_cast<size_t>(2 - tap) * C * 2 * C,
-                                                                 w.w1d + static_cast<size_t>(tap) * 2 * C * C, C, 2 * C);
+        h_wp[l] = w.wp; h_bp[l] = w.bp;
     }
-    CKN(dmalloc(n, &n->wspT, static_cast<size_t>(C) * C));
-    transpose_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wsp_f, n->wspT, C, C);
-    CKN(cudaGetLastError());
     CKN(dmalloc(n, &n->d_wp, layers));
     CKN(dmalloc(n, &n->d_bp, layers));
     CKN(cudaMemcpy(n->d_wp, h_wp.data(), sizeof(float*) * layers, cudaMemcpyHostToDevice));
     CKN(cudaMemcpy(n->d_bp, h_bp.data(), sizeof(float*) * layers, cudaMemcpyHostToDevice));
-
-    // ---- tensor-core packing (C == 256) ----
     if (C == TC_C) {
-        const size_t wtc_elems = static_cast<size_t>(layers) * 32 * 256 * 64;
-        CKN(dmalloc(n, &n->wtc, wtc_elems));
+        CKN(dmalloc(n, &n->wtc, static_cast<size_t>(layers) * 32 * 256 * 64));
         CKN(dmalloc(n, &n->wsp_tc, 4ULL * 256 * 64));
         const long long ldm = static_cast<long long>(layers) * 1536;
         CKN(dmalloc(n, &n->mtab, 512ULL * ldm));
         CKN(dmalloc(n, &n->cvec, static_cast<size_t>(ldm)));
-        float* wpT = nullptr;
-        CKN(cudaMalloc(&wpT, sizeof(float) * 512 * C));
-        for (int l = 0; l < layers; ++l) {
-            LayerW& w = n->L[l];
-            pack_tc_layer_kernel<<<148 * 4, 256>>>(w.w1f, w.w2f, n->wtc + static_cast<size_t>(l) * 32 * 256 * 64);
-            transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, wpT, C, 512);     // [C][512] -> [512][C]
-            for (int tap = 0; tap < 3; ++tap) {
-                ConvF32Args a;
-                memset(&a, 0, sizeof a);
-                // mtab[k][l,tap,co] = sum_ci Wp[ci][k] * W1[tap][ci][co]
-                a.in = wpT; a.w = w.w1f + static_cast<size_t>(tap) * C * 2 * C; a.out = n->mtab + (l * 3 + tap) * 512;
-                a.nb = 1; a.L = 512; a.Cin = C; a.Cout = 2 * C; a.taps = 1; a.dil = 1;
-                a.ldw = 2 * C; a.ldo = ldm; a.in_scale = 1.f;
-                CKN(conv_cl_f32(a, 0));
-                // cvec[l,tap,co] = sum_ci bp[ci] * W1[tap][ci][co] (+ b1[co] for the centre tap)
-                a.in = w.bp; a.out = n->cvec + (l * 3 + tap) * 512; a.L = 1; a.ldo = 2 * C;
-                a.bias = (tap == 1) ? w.b1 : nullptr;
-                CKN(conv_cl_f32(a, 0));
-            }
-            CKN(cudaDeviceSynchronize());      // wpT is reused by the next layer
-        }
-        pack_tc_tail_kernel<<<64, 256>>>(n->wsp_f, n->wsp_tc);
-        CKN(cudaGetLastError());
-        CKN(cudaDeviceSynchronize());
-        cudaFree(wpT);
         int rc2 = make_weight_map(&n->tm_w, n->wtc, static_cast<uint64_t>(layers) * 32 * 256);
         if (!rc2) rc2 = make_weight_map(&n->tm_w2, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 128);
         if (!rc2) rc2 = make_weight_map(&n->tm_w4, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 64);
@@ -561,17 +568,32 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             const char* pe = getenv("ADB_TC_PAIR");
             if (pe) n->pair = atoi(pe) != 0;
         }
-        if (rc2) { adb_wavenet_destroy(n); cudaFree(d_jobs); return rc2; }
+        if (rc2) { adb_wavenet_destroy(n); return rc2; }
         CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
-        n->tc_ready = true;
     }
+    rc = refold(n);
+    if (rc) { adb_wavenet_destroy(n); return rc; }
     CKN(cudaDeviceSynchronize());
-    cudaFree(d_jobs);
 #undef CKN
     *out = n;
     return ADB_OK;
+}
+
+// Replace the parameters of an existing handle (same configuration) and rebuild everything derived from them. Used
+// after an optimizer step: no allocation, kernels only (legacy default stream).
+extern "C" int adb_wavenet_load_params(adb_wavenet* n, const float* params, int64_t n_params, int on_device) {
+    REQUIRE(n && params, "adb_wavenet_load_params: null argument");
+    REQUIRE(n_params == n->n_params, "parameter vector has %lld values, expected %lld", static_cast<long long>(n_params),
+            static_cast<long long>(n->n_params));
+    int64_t src_off = 0;
+    for (size_t i = 0; i < n->counts.size(); ++i) {
+        if (on_device) CK(cudaMemcpyAsync(n->params + n->dst_off[i], params + src_off, sizeof(float) * n->counts[i], cudaMemcpyDeviceToDevice, 0));
+        else CK(cudaMemcpy(n->params + n->dst_off[i], params + src_off, sizeof(float) * n->counts[i], cudaMemcpyHostToDevice));
+        src_off += n->counts[i];
+    }
+    return refold(n);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -265,6 +265,88 @@ def run_unet(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_train(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: DiffWave SC09-shape EDM training step (DSM loss, LogNormal(-1.2, 1.2) sigmas, AdamW
+    lr 1e-4) with one NCCL all-reduce of the flat gradient per step. fp32 CUDA-core kernels in this round."""
+    import torch.distributed as dist
+    from audiodiffuser_b200 import EluDiffusion, WaveNetNoise, _native
+    from audiodiffuser_b200.training import FusedTrainer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or 4
+    torch.manual_seed(0)                                   # identical initial weights on every rank, like DDP's broadcast
+    net = WaveNetNoise(C, LAYERS, CYCLE, precision="fp32")
+    net.output_projection.conv.weight.data.normal_(0.0, 1.0 / 16.0)
+    net = net.to(dev)
+    trainer = FusedTrainer(net, EluDiffusion(sigma_data=SIGMA_DATA), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.01)
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = (torch.randn(B, 1, L, generator=g) * SIGMA_DATA).clamp(-1, 1).pin_memory()
+    sig_host = (torch.randn(B, generator=g) * 1.2 - 1.2).exp().pin_memory()
+    x_dev, sig_dev = x_host.to(dev), sig_host.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        return trainer.step(x_dev, sig_dev)
+
+    def step_e2e():
+        loss = trainer.step(x_host.to(dev, non_blocking=True), sig_host.to(dev, non_blocking=True))
+        return float(loss.mean())                          # device -> host read of the step's result
+
+    for _ in range(max(args.warmup, 1)):
+        loss = step_resident()
+    _native.check_async()
+    assert torch.isfinite(loss).all()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    ms_res = timed(step_resident, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if clocks else None
+    _native.check_async()
+    if rank == 0:
+        total = B * world * args.steps
+        flop_step = 3 * 606.093e9 * B * world
+        line = {"metric": "diffwave_sc09_edm_train_samples_per_sec", "value": total / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"DiffWave C={C} layers={LAYERS} SC09 shape 1x{L}: DSM loss forward + backward + flat-gradient "
+                                       f"all-reduce + AdamW(lr 1e-4, wd 0.01), sigma ~ LogNormal(-1.2, 1.2) (BASELINE.json configs[2])",
+                           "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": f"data-parallel x{world}, one NCCL all-reduce of {trainer.flat.numel() * 4 / 1e6:.1f} MB per step",
+                           "l2": "activations (1.7 GB per sample saved for the backward) >> 126 MB L2"},
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + sig_host.numel() * 4,
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": None, "effective_tflops": flop_step * args.steps / (ms_res * 1e-3) / 1e12, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,7 +354,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 8 UNet1d)")
-    ap.add_argument("--workload", default="diffwave", choices=["diffwave", "unet1d"],
+    ap.add_argument("--workload", default="diffwave", choices=["diffwave", "unet1d", "train"],
                     help="diffwave = the headline metric (BASELINE.json configs[1]); unet1d = configs[3]")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,12 +363,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "unet1d":
+    if args.workload in ("unet1d", "train"):
         if args.impl == "reference":
             if rank == 0:
                 print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the headline DiffWave workload"}))
             return
-        run_unet(args, rank, world, local_rank)
+        (run_unet if args.workload == "unet1d" else run_train)(args, rank, world, local_rank)
         return
     args.batch = args.batch or 256
     if args.impl == "reference":

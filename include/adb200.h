@@ -101,6 +101,9 @@ int64_t adb_wavenet_param_count(int residual_channels, int residual_layers);
  * weight norm (wavenet.py:44-51), packs weights for both precisions. Synchronises. */
 int adb_wavenet_create(adb_wavenet** out, int residual_channels, int residual_layers, int dilation_cycle,
                        const float* params, int64_t n_params, int on_device);
+/* Replace the parameters of an existing handle (same configuration) and rebuild the packed weights without
+ * re-allocating: what a training loop calls after each optimizer step. Enqueues on the legacy default stream. */
+int adb_wavenet_load_params(adb_wavenet* net, const float* params, int64_t n_params, int on_device);
 void adb_wavenet_destroy(adb_wavenet* net);
 /* Bytes of scratch the calls below need for (B, L, precision); the caller owns the buffer. */
 int64_t adb_wavenet_workspace_bytes(const adb_wavenet* net, int B, int L, int precision);
