@@ -135,6 +135,27 @@ def test_config_instantiate():
     assert opt.defaults["lr"] == 1e-4
 
 
+def test_unet_config_instantiate_and_state_dict_layout():
+    """configs/model/unet1d_edm_b200.yaml builds the fused UNet1dBase; its state_dict has the reference's key set
+    (checked against the oracle's shape table, which make_golden_unet.py asserts equal to the reference's)."""
+    from audiodiffuser_b200.config import instantiate, load_yaml
+    from audiodiffuser_b200 import UNet1dBase
+    from oracle.weights import unet1d_param_shapes, UNET_SMALL
+    cfg = load_yaml(os.path.join(ROOT, "configs", "model", "unet1d_edm_b200.yaml"))
+    cfg["net"].update(channels=32, num_filters=32, multipliers=[1, 2, 2], factors=[4, 2], num_blocks=[2, 1],
+                      attentions=[False, True], attention_heads=4, window_length=8, stride=4)     # keep the CPU test light
+    net = instantiate(cfg)["net"]
+    assert isinstance(net, UNet1dBase)
+    want = unet1d_param_shapes(UNET_SMALL)
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert list(got.keys()) == list(want.keys()) and got == dict(want)
+    assert float(net.unet.to_out.to_out.weight.abs().max()) == 0.0             # unet1d.py:619
+    with pytest.raises(NotImplementedError):
+        UNet1dBase(**dict(UNET_SMALL, text_cond=True))
+    with pytest.raises(Exception):
+        net(torch.zeros(1, 2, 64), torch.zeros(1))                             # CPU tensors: no fallback
+
+
 def test_shard_ranges_cover_batch():
     from audiodiffuser_b200.sharding import shard_range
     for gb in (1, 7, 64, 257, 4096):
