@@ -22,6 +22,7 @@
 #include "cl_ops.cuh"
 #include "cl_conv_tc.cuh"
 #include "train_kernels.cuh"
+#include "train_tc.cuh"
 
 using namespace adb;
 

@@ -8,60 +8,81 @@
 // (torch.optim.AdamW semantics, configs/model/diffunet_complex.yaml:7-12).
 #pragma once
 #include "ptx.cuh"
+#include "cl_ops.cuh"
 
 namespace adb {
 
 // out[b][t][c] = h[b][t][c] + p[b][c]   (wavenet.py:108-109, materialised for the weight gradient)
-__global__ void __launch_bounds__(256) add_bcast_kernel(const float* __restrict__ h, const float* __restrict__ p,
-                                                        float* __restrict__ out, int B, int L, int C) {
-    const long long total4 = static_cast<long long>(B) * L * C / 4;
-    const int c4n = C / 4;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+template <typename T>
+__global__ void __launch_bounds__(256) add_bcast_kernel(const T* __restrict__ h, const float* __restrict__ p,
+                                                        T* __restrict__ out, int B, int L, int C) {
+    const long long total = static_cast<long long>(B) * L * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(i % c4n);
-        const int b = static_cast<int>(i / (static_cast<long long>(L) * c4n));
-        float4 v = reinterpret_cast<const float4*>(h)[i];
-        const float4 e = reinterpret_cast<const float4*>(p + static_cast<long long>(b) * C)[c4];
-        v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
-        reinterpret_cast<float4*>(out)[i] = v;
+        const int c = static_cast<int>(i % C);
+        const int b = static_cast<int>(i / (static_cast<long long>(L) * C));
+        cl_st<T>(out + i, cl_ld<T>(h + i) + p[static_cast<long long>(b) * C + c]);
     }
 }
 
-// z = sigmoid(g) tanh(f)  =>  dg = dz tanh(f) s (1 - s),  df = dz s (1 - tanh(f)^2)   (wavenet.py:111-112)
-__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dz,
-                                                       float* __restrict__ dy, long long rows, int C) {
+// z[r][c] = sigmoid(y[r][c]) * tanh(y[r][C + c])   (wavenet.py:111-112), any activation dtype
+template <typename T>
+__global__ void __launch_bounds__(256) gate_t_kernel(const T* __restrict__ y, T* __restrict__ z, long long rows, int C) {
     const long long total = rows * C;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / C;
         const int c = static_cast<int>(i % C);
-        const float g = y[r * 2 * C + c], f = y[r * 2 * C + C + c];
-        const float s = 1.0f / (1.0f + expf(-g)), th = tanhf(f), d = dz[i];
-        dy[r * 2 * C + c] = d * th * s * (1.0f - s);
-        dy[r * 2 * C + C + c] = d * s * (1.0f - th * th);
+        const float g = cl_ld<T>(y + r * 2 * C + c), f = cl_ld<T>(y + r * 2 * C + C + c);
+        cl_st<T>(z + i, (1.0f / (1.0f + expf(-g))) * tanhf(f));
+    }
+}
+
+// z = sigmoid(g) tanh(f)  =>  dg = dz tanh(f) s (1 - s),  df = dz s (1 - tanh(f)^2)   (wavenet.py:111-112)
+template <typename T>
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dz,
+                                                       T* __restrict__ dy, long long rows, int C) {
+    const long long total = rows * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / C;
+        const int c = static_cast<int>(i % C);
+        const float g = cl_ld<T>(y + r * 2 * C + c), f = cl_ld<T>(y + r * 2 * C + C + c);
+        const float s = 1.0f / (1.0f + expf(-g)), th = tanhf(f), d = cl_ld<T>(dz + i);
+        cl_st<T>(dy + r * 2 * C + c, d * th * s * (1.0f - s));
+        cl_st<T>(dy + r * 2 * C + C + c, d * s * (1.0f - th * th));
     }
 }
 
 // do[r][0:C] = dh_out[r] / sqrt(2) (0 if dh_out == nullptr: the last block's residual output is unused) ; do[r][C:2C] = dskip[r]
 // (wavenet.py:114-115, :149)
-__global__ void __launch_bounds__(256) build_do_kernel(const float* __restrict__ dh_out, const float* __restrict__ dskip,
-                                                       float* __restrict__ dout, long long rows, int C) {
+template <typename T>
+__global__ void __launch_bounds__(256) build_do_kernel(const T* __restrict__ dh_out, const T* __restrict__ dskip,
+                                                       T* __restrict__ dout, long long rows, int C) {
     const long long total = rows * C;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / C;
         const int c = static_cast<int>(i % C);
-        dout[r * 2 * C + c] = dh_out ? dh_out[i] * 0.70710678118654752f : 0.f;
+        cl_st<T>(dout + r * 2 * C + c, dh_out ? cl_ld<T>(dh_out + i) * 0.70710678118654752f : 0.f);
         dout[r * 2 * C + C + c] = dskip[i];
     }
 }
 
 // out = a * x + b * y (y may be nullptr)
-__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float b,
-                                                    float* __restrict__ out, long long n) {
+template <typename T>
+__global__ void __launch_bounds__(256) axpby_kernel(const T* __restrict__ x, float a, const T* __restrict__ y, float b,
+                                                    T* __restrict__ out, long long n) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
-        out[i] = y ? fmaf(a, x[i], b * y[i]) : a * x[i];
+        cl_st<T>(out + i, y ? fmaf(a, cl_ld<T>(x + i), b * cl_ld<T>(y + i)) : a * cl_ld<T>(x + i));
+}
+
+// dst (bf16) = src (fp32)
+__global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = __float2bfloat16_rn(in[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -120,8 +141,9 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const float* __restrict_
             atomicAdd(out + static_cast<long long>(i0 + ty * 4 + i) * ldo + j0 + tx * 4 + j, acc[i][j] * a_scale);
 }
 
-// Column sums: out[(per_sample ? b : 0)][c] += sum_t in[b][t][c]. grid (chunks, nb), 256 threads, C % 4 == 0, C <= 1024.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, float* __restrict__ out, int L, int C,
+// Column sums: out[(per_sample ? b : 0)][c] += sum_t in[b][t][c]. grid (chunks, nb), 256 threads, C <= 1024.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, float* __restrict__ out, int L, int C,
                                                      int chunks, int per_sample) {
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int rows_per = (L + chunks - 1) / chunks;
@@ -129,17 +151,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ i
     __shared__ float red[1024];
     for (int c = threadIdx.x; c < C; c += blockDim.x) red[c] = 0.f;
     __syncthreads();
-    const int c4n = C / 4;
-    const int rstep = max(1, 256 / c4n), rofs = threadIdx.x / c4n;
+    const int rstep = max(1, 256 / C), rofs = threadIdx.x / C;
     if (rofs < rstep) {
-        for (int c4 = threadIdx.x % c4n; c4 < c4n; c4 += 256) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = r0 + rofs; r < r1; r += rstep) {
-                const float4 v = *reinterpret_cast<const float4*>(in + (static_cast<long long>(b) * L + r) * C + c4 * 4);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            }
-            atomicAdd(&red[c4 * 4], s.x); atomicAdd(&red[c4 * 4 + 1], s.y);
-            atomicAdd(&red[c4 * 4 + 2], s.z); atomicAdd(&red[c4 * 4 + 3], s.w);
+        for (int c = threadIdx.x % C; c < C; c += 256) {
+            float s = 0.f;
+            for (int r = r0 + rofs; r < r1; r += rstep) s += cl_ld<T>(in + (static_cast<long long>(b) * L + r) * C + c);
+            atomicAdd(&red[c], s);
         }
     }
     __syncthreads();
@@ -179,7 +196,8 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__
 
 // Input projection backward (wavenet.py:172-174): h0 = relu(w_in x~ + b_in):
 //   dw_in[c] += sum_r [h0 > 0] dh0[r][c] x~[r] ; db_in[c] += sum_r [h0 > 0] dh0[r][c] ; x~[r] = scale_b x[r]
-__global__ void __launch_bounds__(256) inproj_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ h0,
+template <typename T>
+__global__ void __launch_bounds__(256) inproj_bwd_kernel(const T* __restrict__ dh0, const T* __restrict__ h0,
                                                          const float* __restrict__ x, const float* __restrict__ scale,
                                                          float* __restrict__ dw_in, float* __restrict__ db_in, int L,
                                                          long long rows, int C) {
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(256) inproj_bwd_kernel(const float* __restrict
     const int rstep = blockDim.x / C, rofs = threadIdx.x / C;
     float lw = 0.f, lb = 0.f;
     for (long long r = static_cast<long long>(blockIdx.x) * rstep + rofs; r < rows; r += static_cast<long long>(gridDim.x) * rstep) {
-        const float m = h0[r * C + c] > 0.f ? dh0[r * C + c] : 0.f;
+        const float m = cl_ld<T>(h0 + r * C + c) > 0.f ? cl_ld<T>(dh0 + r * C + c) : 0.f;
         const float xv = __fmul_rn(scale[r / L], x[r]);
         lw = fmaf(m, xv, lw);
         lb += m;

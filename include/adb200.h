@@ -175,6 +175,11 @@ int adb_cl_conv(const void* in_dev, const void* w_dev, const float* bias_dev, co
                 int dtype, void* stream);
 int64_t adb_cl_conv_packed_elems(int Cin, int N, int taps);
 int adb_cl_pack_conv_weights(const float* w_f32_dev, void* packed_bf16_dev, int Cin, int N, int taps, void* stream);
+/* Weight gradient of the same convolution (what autograd computes for nn.Conv1d weights): out[tap][i][j] (fp32
+ * [taps][Ca][Cg], accumulated into) += scale * sum_{b,t} A[b][t + (tap - taps/2)*dil][i] * G[b][t][j], rows of A
+ * outside [0, L) read as zero. ADB_DTYPE_BF16: tcgen05 with MN-major operands straight from the channels-last tensors. */
+int adb_cl_wgrad(const void* a_dev, const void* g_dev, float* out_dev, int B, int L, int Ca, int Cg, int taps, int dil,
+                 float scale, int dtype, void* stream);
 /* out[b][n] = act(bias[n] + sum_k W[n][k] * f(in[b][k])), f = SiLU if silu_in; fp32 (time MLP unet1d.py:678-684,
  * to_cond_embedding :271-276, :304-308) */
 int adb_cl_linear(const float* in_dev, const float* w_dev, const float* bias_dev, float* out_dev, int B, int K, int N,

@@ -106,3 +106,28 @@ def test_training_steps_reduce_loss(dev):
         losses.append(float(loss.detach()))
     print('losses', losses)
     assert losses[-1] < 0.9 * losses[0] and min(losses) == min(losses[10:]), losses
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,L,Ca,Cg,taps,dil", [(2, 300, 256, 512, 3, 4), (1, 1000, 128, 256, 1, 1), (3, 77, 256, 512, 3, 64)])
+def test_wgrad_gemm(dev, dtype, B, L, Ca, Cg, taps, dil):
+    """adb_cl_wgrad (CUDA-core fp32 and tcgen05 bf16 with MN-major operands) against an fp64 einsum."""
+    from audiodiffuser_b200 import _native as N
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    a = torch.randn(B, L, Ca, generator=g)
+    gr = torch.randn(B, L, Cg, generator=g)
+    dt, adt = (1, torch.bfloat16) if dtype == "bf16" else (0, torch.float32)
+    a_d, g_d = a.to(dev).to(adt), gr.to(dev).to(adt)
+    a64, g64 = a_d.double().cpu(), g_d.double().cpu()        # the rounded operands, so only accumulation differs
+    want = torch.zeros(taps, Ca, Cg, dtype=torch.float64)
+    for tap in range(taps):
+        sh = (tap - taps // 2) * dil
+        lo, hi = max(0, -sh), min(L, L - sh)
+        if hi > lo:
+            want[tap] = torch.einsum("bti,btj->ij", a64[:, lo + sh:hi + sh], g64[:, lo:hi])
+    out = torch.zeros(taps, Ca, Cg, device=dev)
+    N.check(N.lib().adb_cl_wgrad(N.ptr(a_d), N.ptr(g_d), N.ptr(out), B, L, Ca, Cg, taps, dil, 0.5, dt, N.stream_ptr(dev)))
+    N.check_async()
+    e = rel_l2(out, want * 0.5)
+    print(f"wgrad {dtype} {B}x{L} {Ca}->{Cg} taps {taps} dil {dil}: rel-L2 {e:.3e}")
+    assert e < 2e-5
