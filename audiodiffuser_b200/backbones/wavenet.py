@@ -260,12 +260,13 @@ class _DsmLossFn(torch.autograd.Function):
         lib = N.lib()
         B, _, L = x.shape
         h = net._native()
-        nbytes = lib.adb_wavenet_train_workspace_bytes(h, B, L)
+        prec = net._prec()
+        nbytes = lib.adb_wavenet_train_workspace_bytes(h, B, L, prec)
         ws_buf, ws = N.alloc_workspace(nbytes, x.device)
         loss = torch.empty(B, dtype=torch.float32, device=x.device)
         N.check(lib.adb_wavenet_dsm_forward_train(h, N.ptr(x), N.ptr(noise), N.ptr(sigmas), sigma_data, N.ptr(loss), B, L,
-                                                  ws, nbytes, N.stream_ptr(x.device)))
-        ctx.net, ctx.ws, ctx.ws_buf, ctx.nbytes, ctx.sigma_data = net, ws, ws_buf, nbytes, sigma_data
+                                                  prec, ws, nbytes, N.stream_ptr(x.device)))
+        ctx.net, ctx.ws, ctx.ws_buf, ctx.nbytes, ctx.sigma_data, ctx.prec = net, ws, ws_buf, nbytes, sigma_data, prec
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.save_for_backward(x, sigmas)
         return loss
@@ -279,7 +280,7 @@ class _DsmLossFn(torch.autograd.Function):
         flat = torch.empty(n_params, dtype=torch.float32, device=x.device)
         up = N.require_cuda_f32(grad_loss, "grad_loss").reshape(B)
         N.check(lib.adb_wavenet_dsm_backward(net._native(), N.ptr(x), N.ptr(sigmas), ctx.sigma_data, N.ptr(up), N.ptr(flat), B, L,
-                                             ctx.ws, ctx.nbytes, N.stream_ptr(x.device)))
+                                             ctx.prec, ctx.ws, ctx.nbytes, N.stream_ptr(x.device)))
         ctx.ws = ctx.ws_buf = None
         grads, off = [], 0
         for shp in ctx.shapes:

@@ -245,6 +245,8 @@ struct LayerW {
     float *w1f, *w2f;
     // transposed / tap-reversed copies for the data-gradient convolutions (training step)
     float *w2T, *w1d;
+    // the same three matrices packed for cl_conv_tc_kernel (bf16 training step): forward recompute, dz, dx
+    __nv_bfloat16 *w1p, *w2Tp, *w1dp;
 };
 
 struct TimerPair {
@@ -433,6 +435,9 @@ static int refold(adb_wavenet* n) {
         for (int l = 0; l < layers; ++l) {
             LayerW& w = n->L[l];
             pack_tc_layer_kernel<<<148 * 4, 256>>>(w.w1f, w.w2f, n->wtc + static_cast<size_t>(l) * 32 * 256 * 64);
+            cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1f, w.w1p, C, 2 * C, 3);
+            cl_pack_conv_tc_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2T, w.w2Tp, 2 * C, C, 1);
+            cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1d, w.w1dp, 2 * C, C, 3);
             transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, n->wpT, C, 512);     // [C][512] -> [512][C] (stream-ordered reuse)
             for (int tap = 0; tap < 3; ++tap) {
                 ConvF32Args a;
@@ -546,6 +551,12 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(dmalloc(n, &w.w2f, 2ULL * C * C));
         CKN(dmalloc(n, &w.w2T, 2ULL * C * C));
         CKN(dmalloc(n, &w.w1d, 3ULL * 2 * C * C));
+        w.w1p = w.w2Tp = w.w1dp = nullptr;
+        if (C == TC_C) {
+            CKN(dmalloc(n, &w.w1p, 3ULL * C * 2 * C));
+            CKN(dmalloc(n, &w.w2Tp, 2ULL * C * C));
+            CKN(dmalloc(n, &w.w1dp, 3ULL * 2 * C * C));
+        }
         h_wp[l] = w.wp; h_bp[l] = w.bp;
     }
     CKN(dmalloc(n, &n->d_wp, layers));
@@ -693,7 +704,8 @@ static int check_forward_args(adb_wavenet* n, int B, int L, int precision, void*
 
 static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, const float* in_scale, int in_scale_stride,
                         float* out, int B, int L, int precision, const Workspace& w, float* dump_h, float* dump_skip,
-                        int dump_layers, cudaStream_t st) {
+                        int dump_layers, cudaStream_t st, __nv_bfloat16* h_save = nullptr) {
+    // h_save (bf16 path, training): [layers][B][L][C]; block l reads slot l and writes slot l + 1 instead of ping-ponging
     const int C = n->C, layers = n->layers;
     const long long BL = static_cast<long long>(B) * L;
     {
@@ -756,7 +768,8 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
         a.nb = 1; a.L = B; a.Cin = 512; a.Cout = layers * 1536; a.taps = 1; a.dil = 1;
         a.ldw = static_cast<long long>(layers) * 1536; a.ldo = a.ldw; a.in_scale = 1.f;
         CK(conv_cl_f32(a, st));
-        in_proj_kernel<true><<<grid_for(BL * (C / 8)), 256, 0, st>>>(x, in_scale, in_scale_stride, n->w_in_f, n->b_in, w.hbA,
+        in_proj_kernel<true><<<grid_for(BL * (C / 8)), 256, 0, st>>>(x, in_scale, in_scale_stride, n->w_in_f, n->b_in,
+                                                                     h_save ? h_save : w.hbA,
                                                                      B, L, C);
         CK(cudaGetLastError());
     }
@@ -784,7 +797,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     }
     const int groups = (num_tiles + cl - 1) / cl;
     const int grid_block = (groups < max_clusters ? groups : max_clusters) * cl;
-    __nv_bfloat16 *hin = w.hbA, *hout = w.hbB;
+    __nv_bfloat16 *hin = h_save ? h_save : w.hbA, *hout = (h_save && layers > 1) ? h_save + BL * C : w.hbB;
     for (int l = 0; l < layers; ++l) {
         ScopedTimer t(n, ADB_TIMER_CONV, st);
         CUtensorMap m_h, m_hout, m_skip;
@@ -824,7 +837,8 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
             cvt_bf16_f32_kernel<<<grid_for(BL * C), 256, 0, st>>>(hout, dump_h + l * BL * C, BL * C);
             CK(cudaMemcpyAsync(dump_skip + l * BL * C, w.skip, sizeof(float) * BL * C, cudaMemcpyDeviceToDevice, st));
         }
-        __nv_bfloat16* tmp = hin; hin = hout; hout = tmp;
+        if (h_save) { hin = hout; hout = (l + 2 < layers) ? hin + BL * C : w.hbB; }
+        else { __nv_bfloat16* tmp = hin; hin = hout; hout = tmp; }
     }
     {
         ScopedTimer t(n, ADB_TIMER_TAIL, st);

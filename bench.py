@@ -267,7 +267,8 @@ def run_unet(args, rank, world, local_rank):
 
 def run_train(args, rank, world, local_rank):
     """BASELINE.json configs[2]: DiffWave SC09-shape EDM training step (DSM loss, LogNormal(-1.2, 1.2) sigmas, AdamW
-    lr 1e-4) with one NCCL all-reduce of the flat gradient per step. fp32 CUDA-core kernels in this round."""
+    lr 1e-4) with one NCCL all-reduce of the flat gradient per step. --precision bf16: tcgen05 forward / dgrad / wgrad
+    GEMMs (bf16 operands, fp32 accumulate and fp32 master weights); --precision fp32: CUDA-core kernels."""
     import torch.distributed as dist
     from audiodiffuser_b200 import EluDiffusion, WaveNetNoise, _native
     from audiodiffuser_b200.training import FusedTrainer
@@ -276,9 +277,9 @@ def run_train(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or 4
+    B = args.batch or (16 if args.precision == "bf16" else 4)
     torch.manual_seed(0)                                   # identical initial weights on every rank, like DDP's broadcast
-    net = WaveNetNoise(C, LAYERS, CYCLE, precision="fp32")
+    net = WaveNetNoise(C, LAYERS, CYCLE, precision=args.precision)
     net.output_projection.conv.weight.data.normal_(0.0, 1.0 / 16.0)
     net = net.to(dev)
     trainer = FusedTrainer(net, EluDiffusion(sigma_data=SIGMA_DATA), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.01)
@@ -333,12 +334,12 @@ def run_train(args, rank, world, local_rank):
         flop_step = 3 * 606.093e9 * B * world
         line = {"metric": "diffwave_sc09_edm_train_samples_per_sec", "value": total / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": f"DiffWave C={C} layers={LAYERS} SC09 shape 1x{L}: DSM loss forward + backward + flat-gradient "
                                        f"all-reduce + AdamW(lr 1e-4, wd 0.01), sigma ~ LogNormal(-1.2, 1.2) (BASELINE.json configs[2])",
                            "batch_per_gpu": B, "global_batch": B * world,
                            "parallelism": f"data-parallel x{world}, one NCCL all-reduce of {trainer.flat.numel() * 4 / 1e6:.1f} MB per step",
-                           "l2": "activations (1.7 GB per sample saved for the backward) >> 126 MB L2"},
+                           "l2": "saved activations (0.3 GB bf16 / 1.7 GB fp32 per sample) >> 126 MB L2"},
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + sig_host.numel() * 4,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": None, "effective_tflops": flop_step * args.steps / (ms_res * 1e-3) / 1e12, "clocks": clk}

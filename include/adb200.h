@@ -209,17 +209,20 @@ int adb_cl_wavdec(const void* h_dev, const float* w_dev, float* y_dev, int B, in
 
 /* ------------------------------------------------------------------------------------------------
  * Training step — Diffusion.forward (src/models/components/diffusion.py:65-97) through WaveNetNoise with the
- * backward pass PyTorch autograd would build, AdamW (configs/model/diffunet_complex.yaml:7-12). fp32.
+ * backward pass PyTorch autograd would build, AdamW (configs/model/diffunet_complex.yaml:7-12).
+ * ADB_PRECISION_FP32: CUDA-core kernels, gradients <= 2e-4 relative to the fp64 evaluation of the same graph.
+ * ADB_PRECISION_BF16: tcgen05 forward / data-gradient / weight-gradient GEMMs with bf16 operands and fp32 accumulation
+ * (the precision of Lightning's bf16-mixed), block inputs saved, pre-gate activations recomputed.
  * ---------------------------------------------------------------------------------------------- */
-int64_t adb_wavenet_train_workspace_bytes(const adb_wavenet* net, int B, int L);
+int64_t adb_wavenet_train_workspace_bytes(const adb_wavenet* net, int B, int L, int precision);
 /* loss[b] = lambda(sigma_b) mean (D(x + sigma_b noise) - x)^2, keeping the activations the backward needs in `workspace_dev` */
 int adb_wavenet_dsm_forward_train(adb_wavenet* net, const float* x_dev, const float* noise_dev, const float* sigmas_dev,
-                                  float sigma_data, float* loss_dev, int B, int L, void* workspace_dev, int64_t workspace_bytes,
-                                  void* stream);
+                                  float sigma_data, float* loss_dev, int B, int L, int precision, void* workspace_dev,
+                                  int64_t workspace_bytes, void* stream);
 /* grad_flat[i] = d(sum_b upstream[b] loss[b]) / d(param_i), parameters in the flat order of adb_wavenet_param_count.
  * Must follow adb_wavenet_dsm_forward_train on the same workspace (same x, sigmas). */
 int adb_wavenet_dsm_backward(adb_wavenet* net, const float* x_dev, const float* sigmas_dev, float sigma_data,
-                             const float* upstream_dev, float* grad_flat_dev, int B, int L, void* workspace_dev,
+                             const float* upstream_dev, float* grad_flat_dev, int B, int L, int precision, void* workspace_dev,
                              int64_t workspace_bytes, void* stream);
 /* torch.optim.AdamW update on flat fp32 vectors; gradients are multiplied by grad_scale first (1 / world for DDP averaging) */
 int adb_adamw_step(float* params_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr,
