@@ -12,29 +12,43 @@
 
 namespace adb {
 
+// All element-wise kernels below work on 16-byte vectors (ClVec<T>: 4 floats or 8 bf16) of one row, with 32-bit
+// index math (rows * C / VE < 2^31 is checked by the caller).
+
 // out[b][t][c] = h[b][t][c] + p[b][c]   (wavenet.py:108-109, materialised for the weight gradient)
 template <typename T>
 __global__ void __launch_bounds__(256) add_bcast_kernel(const T* __restrict__ h, const float* __restrict__ p,
                                                         T* __restrict__ out, int B, int L, int C) {
-    const long long total = static_cast<long long>(B) * L * C;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % C);
-        const int b = static_cast<int>(i / (static_cast<long long>(L) * C));
-        cl_st<T>(out + i, cl_ld<T>(h + i) + p[static_cast<long long>(b) * C + c]);
+    constexpr int VE = ClVec<T>::N;
+    const int vpr = C / VE;
+    const unsigned total = static_cast<unsigned>(B) * L * vpr;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / vpr, v = i - r * vpr;
+        const unsigned b = r / L;
+        float x[VE];
+        ClVec<T>::load(h + static_cast<size_t>(i) * VE, x);
+        const float* pp = p + static_cast<size_t>(b) * C + v * VE;
+#pragma unroll
+        for (int k = 0; k < VE; ++k) x[k] += pp[k];
+        ClVec<T>::store(out + static_cast<size_t>(i) * VE, x);
     }
 }
 
 // z[r][c] = sigmoid(y[r][c]) * tanh(y[r][C + c])   (wavenet.py:111-112), any activation dtype
 template <typename T>
 __global__ void __launch_bounds__(256) gate_t_kernel(const T* __restrict__ y, T* __restrict__ z, long long rows, int C) {
-    const long long total = rows * C;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / C;
-        const int c = static_cast<int>(i % C);
-        const float g = cl_ld<T>(y + r * 2 * C + c), f = cl_ld<T>(y + r * 2 * C + C + c);
-        cl_st<T>(z + i, (1.0f / (1.0f + expf(-g))) * tanhf(f));
+    constexpr int VE = ClVec<T>::N;
+    const int vpr = C / VE;
+    const unsigned total = static_cast<unsigned>(rows) * vpr;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / vpr, v = i - r * vpr;
+        const T* yr = y + static_cast<size_t>(r) * 2 * C + v * VE;
+        float g[VE], f[VE];
+        ClVec<T>::load(yr, g);
+        ClVec<T>::load(yr + C, f);
+#pragma unroll
+        for (int k = 0; k < VE; ++k) g[k] = __fdividef(1.0f, 1.0f + __expf(-g[k])) * tanh_fast(f[k]);
+        ClVec<T>::store(z + static_cast<size_t>(i) * VE, g);
     }
 }
 
@@ -42,15 +56,27 @@ __global__ void __launch_bounds__(256) gate_t_kernel(const T* __restrict__ y, T*
 template <typename T>
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dz,
                                                        T* __restrict__ dy, long long rows, int C) {
-    const long long total = rows * C;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / C;
-        const int c = static_cast<int>(i % C);
-        const float g = cl_ld<T>(y + r * 2 * C + c), f = cl_ld<T>(y + r * 2 * C + C + c);
-        const float s = 1.0f / (1.0f + expf(-g)), th = tanhf(f), d = cl_ld<T>(dz + i);
-        cl_st<T>(dy + r * 2 * C + c, d * th * s * (1.0f - s));
-        cl_st<T>(dy + r * 2 * C + C + c, d * s * (1.0f - th * th));
+    constexpr int VE = ClVec<T>::N;
+    constexpr bool FAST = (VE == 8);                 // bf16 path: MUFU exp / tanh (error far below the bf16 rounding)
+    const int vpr = C / VE;
+    const unsigned total = static_cast<unsigned>(rows) * vpr;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / vpr, v = i - r * vpr;
+        const T* yr = y + static_cast<size_t>(r) * 2 * C + v * VE;
+        float g[VE], f[VE], d[VE];
+        ClVec<T>::load(yr, g);
+        ClVec<T>::load(yr + C, f);
+        ClVec<T>::load(dz + static_cast<size_t>(i) * VE, d);
+#pragma unroll
+        for (int k = 0; k < VE; ++k) {
+            const float s = FAST ? __fdividef(1.0f, 1.0f + __expf(-g[k])) : 1.0f / (1.0f + expf(-g[k]));
+            const float th = FAST ? tanh_fast(f[k]) : tanhf(f[k]);
+            g[k] = d[k] * th * s * (1.0f - s);
+            f[k] = d[k] * s * (1.0f - th * th);
+        }
+        T* dr = dy + static_cast<size_t>(r) * 2 * C + v * VE;
+        ClVec<T>::store(dr, g);
+        ClVec<T>::store(dr + C, f);
     }
 }
 
@@ -59,23 +85,46 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const T* __restrict__ y, 
 template <typename T>
 __global__ void __launch_bounds__(256) build_do_kernel(const T* __restrict__ dh_out, const T* __restrict__ dskip,
                                                        T* __restrict__ dout, long long rows, int C) {
-    const long long total = rows * C;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / C;
-        const int c = static_cast<int>(i % C);
-        cl_st<T>(dout + r * 2 * C + c, dh_out ? cl_ld<T>(dh_out + i) * 0.70710678118654752f : 0.f);
-        dout[r * 2 * C + C + c] = dskip[i];
+    constexpr int VE = ClVec<T>::N;
+    const int vpr = C / VE;
+    const unsigned total = static_cast<unsigned>(rows) * vpr;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / vpr, v = i - r * vpr;
+        float a[VE], s[VE];
+        if (dh_out) {
+            ClVec<T>::load(dh_out + static_cast<size_t>(i) * VE, a);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) a[k] *= 0.70710678118654752f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < VE; ++k) a[k] = 0.f;
+        }
+        ClVec<T>::load(dskip + static_cast<size_t>(i) * VE, s);
+        T* dr = dout + static_cast<size_t>(r) * 2 * C + v * VE;
+        ClVec<T>::store(dr, a);
+        ClVec<T>::store(dr + C, s);
     }
 }
 
-// out = a * x + b * y (y may be nullptr)
+// out = a * x + b * y (y may be nullptr); n % VE == 0
 template <typename T>
 __global__ void __launch_bounds__(256) axpby_kernel(const T* __restrict__ x, float a, const T* __restrict__ y, float b,
                                                     T* __restrict__ out, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        cl_st<T>(out + i, y ? fmaf(a, cl_ld<T>(x + i), b * cl_ld<T>(y + i)) : a * cl_ld<T>(x + i));
+    constexpr int VE = ClVec<T>::N;
+    const unsigned total = static_cast<unsigned>(n / VE);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float xv[VE], yv[VE];
+        ClVec<T>::load(x + static_cast<size_t>(i) * VE, xv);
+        if (y) {
+            ClVec<T>::load(y + static_cast<size_t>(i) * VE, yv);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) xv[k] = fmaf(a, xv[k], b * yv[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < VE; ++k) xv[k] *= a;
+        }
+        ClVec<T>::store(out + static_cast<size_t>(i) * VE, xv);
+    }
 }
 
 // dst (bf16) = src (fp32)
@@ -141,26 +190,34 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const float* __restrict_
             atomicAdd(out + static_cast<long long>(i0 + ty * 4 + i) * ldo + j0 + tx * 4 + j, acc[i][j] * a_scale);
 }
 
-// Column sums: out[(per_sample ? b : 0)][c] += sum_t in[b][t][c]. grid (chunks, nb), 256 threads, C <= 1024.
+// Column sums: out[(per_sample ? b : 0)][c] += sum_t in[b][t][c]. grid (chunks, nb), 256 threads; a thread owns one
+// 16-byte channel vector and strides over the rows of its chunk. C <= 1024, 256 % (C / VE) == 0.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, float* __restrict__ out, int L, int C,
                                                      int chunks, int per_sample) {
+    constexpr int VE = ClVec<T>::N;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int rows_per = (L + chunks - 1) / chunks;
     const int r0 = chunk * rows_per, r1 = min(L, r0 + rows_per);
     __shared__ float red[1024];
     for (int c = threadIdx.x; c < C; c += blockDim.x) red[c] = 0.f;
     __syncthreads();
-    const int rstep = max(1, 256 / C), rofs = threadIdx.x / C;
-    if (rofs < rstep) {
-        for (int c = threadIdx.x % C; c < C; c += 256) {
-            float s = 0.f;
-            for (int r = r0 + rofs; r < r1; r += rstep) s += cl_ld<T>(in + (static_cast<long long>(b) * L + r) * C + c);
-            atomicAdd(&red[c], s);
-        }
+    const int vpr = C / VE;
+    const int rstep = 256 / vpr, rofs = threadIdx.x / vpr, v = threadIdx.x % vpr;
+    float s[VE];
+#pragma unroll
+    for (int k = 0; k < VE; ++k) s[k] = 0.f;
+    const T* col = in + static_cast<size_t>(b) * L * C + v * VE;
+    for (int r = r0 + rofs; r < r1; r += rstep) {
+        float x[VE];
+        ClVec<T>::load(col + static_cast<size_t>(r) * C, x);
+#pragma unroll
+        for (int k = 0; k < VE; ++k) s[k] += x[k];
     }
+#pragma unroll
+    for (int k = 0; k < VE; ++k) atomicAdd(&red[v * VE + k], s[k]);
     __syncthreads();
-    float* o = out + (per_sample ? static_cast<long long>(b) * C : 0);
+    float* o = out + (per_sample ? static_cast<size_t>(b) * C : 0);
     for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(o + c, red[c]);
 }
 
