@@ -168,6 +168,7 @@ class UNet1dBase(nn.Module):
         self._packed_key = None
         self._graphs = {}
         self.use_cuda_graph = True
+        self.graph_launches = 0          # kernel launches replayed through CUDA graphs (invisible to adb_launch_count)
 
     # ---- weight re-layout (once per parameter version) ----------------------------------------------
     def _param_key(self):
@@ -435,11 +436,14 @@ class UNet1dBase(nn.Module):
                 self._run(sx, stt, so)                          # warm-up outside capture (tensor-map cache, attributes)
             torch.cuda.current_stream(x.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            before = N.lib().adb_launch_count(0)
             with torch.cuda.graph(graph):
                 self._run(sx, stt, so)
-            g = self._graphs[key] = (graph, sx, stt, so)
-        graph, sx, stt, so = g
+            per_replay = N.lib().adb_launch_count(0) - before
+            g = self._graphs[key] = (graph, sx, stt, so, per_replay)
+        graph, sx, stt, so, per_replay = g
         sx.copy_(x)
         stt.copy_(t)
         graph.replay()
+        self.graph_launches += per_replay
         return so.clone()

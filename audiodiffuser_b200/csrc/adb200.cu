@@ -53,6 +53,16 @@ static int fail(int code, const char* fmt, ...) {
         if (!(cond)) return fail(ADB_ERR_INVALID, __VA_ARGS__); \
     } while (0)
 
+// Kernel launches issued by the op-level entry points (adb_edm_*, adb_cl_*, training step); the DiffWave handle keeps its
+// own per-class counters (adb_wavenet_timers). bench.py reports their sum as gpu_launches.
+static long long g_launches = 0;
+#define KL(n) (g_launches += (n))
+extern "C" long long adb_launch_count(int reset) {
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
 extern "C" const char* adb_last_error(void) { return g_err.c_str(); }
 extern "C" int adb_version(void) { return 100; }
 
@@ -113,8 +123,9 @@ extern "C" int adb_edm_precond_in(const float* x, const float* sigmas, int sigma
     REQUIRE(sigma_stride == 0 || sigma_stride == 1, "sigma_stride must be 0 or 1");
     EdmArgs p = edm_args(x, nullptr, nullptr, net_in, nullptr, n_per, n_per * B);
     p.sigmas = sigmas; p.sigma_stride = sigma_stride; p.sigma_data = sigma_data; p.sd2 = sd2_of(sigma_data);
-    CK(edm_launch<OP_SCALE_IN>(p, nullptr, S(stream)));
+    KL(1); CK(edm_launch<OP_SCALE_IN>(p, nullptr, S(stream)));
     if (c_noise) {
+        KL(1);
         edm_cnoise_kernel<<<(B + 255) / 256, 256, 0, S(stream)>>>(sigmas, sigma_stride, c_noise, B);
         CK(cudaGetLastError());
     }
@@ -129,6 +140,7 @@ extern "C" int adb_edm_precond_out(const float* x, const float* f, const float* 
     EdmArgs p = edm_args(x, f, f_null, out, nullptr, n_per, n_per * B);
     p.sigmas = sigmas; p.sigma_stride = sigma_stride; p.sigma_data = sigma_data; p.sd2 = sd2_of(sigma_data);
     p.cond_scale = cond_scale;
+    KL(1);
     if (f_null) CK(edm_launch<OP_COMBINE_CFG>(p, nullptr, S(stream)));
     else        CK(edm_launch<OP_COMBINE>(p, nullptr, S(stream)));
     return ADB_OK;
@@ -138,7 +150,7 @@ extern "C" int adb_edm_scale(const float* x, float a, float* out, int64_t n, voi
     REQUIRE(x && out && n > 0, "adb_edm_scale: bad arguments");
     EdmArgs p = edm_args(x, nullptr, nullptr, out, nullptr, n, n);
     p.a = a;
-    CK(edm_launch<OP_SCALE>(p, nullptr, S(stream)));
+    KL(1); CK(edm_launch<OP_SCALE>(p, nullptr, S(stream)));
     return ADB_OK;
 }
 
@@ -146,7 +158,7 @@ extern "C" int adb_edm_axpy(const float* x, const float* e, float a, float* out,
     REQUIRE(x && e && out && n > 0, "adb_edm_axpy: bad arguments");
     EdmArgs p = edm_args(x, e, nullptr, out, nullptr, n, n);
     p.a = a;
-    CK(edm_launch<OP_AXPY>(p, nullptr, S(stream)));
+    KL(1); CK(edm_launch<OP_AXPY>(p, nullptr, S(stream)));
     return ADB_OK;
 }
 
@@ -155,7 +167,7 @@ extern "C" int adb_edm_euler(const float* x, const float* den, float sigma, floa
     REQUIRE(x && den && d && x_next && n > 0, "adb_edm_euler: bad arguments");
     EdmArgs p = edm_args(x, den, nullptr, d, x_next, n, n);
     p.s0 = sigma; p.h = h;
-    CK(edm_launch<OP_EULER>(p, nullptr, S(stream)));
+    KL(1); CK(edm_launch<OP_EULER>(p, nullptr, S(stream)));
     return ADB_OK;
 }
 
@@ -166,9 +178,9 @@ extern "C" int adb_edm_rk2(const float* x, const float* d, const float* x1, cons
     p.s1 = sigma1; p.h = h; p.w0 = w0; p.w1 = w1;
     if (w0 == 0.5f && w1 == 0.5f) {
         p.hh = 0.5f * h;                       // 0.5 * (sigma_next - sigma_hat), sampler_edm.py:367
-        CK(edm_launch<OP_HEUN>(p, d, S(stream)));
+        KL(1); CK(edm_launch<OP_HEUN>(p, d, S(stream)));
     } else {
-        CK(edm_launch<OP_RK2>(p, d, S(stream)));
+        KL(1); CK(edm_launch<OP_RK2>(p, d, S(stream)));
     }
     return ADB_OK;
 }
@@ -179,7 +191,7 @@ extern "C" int adb_edm_heun_mid(const float* x, const float* f1, float sigma, fl
     const PrecondCoef c = precond_coef(sigma, sigma_data, sd2_of(sigma_data));
     EdmArgs p = edm_args(x, f1, nullptr, d, x1, n, n);
     p.s0 = sigma; p.h = h; p.c_skip0 = c.c_skip; p.c_out0 = c.c_out;
-    CK(edm_launch<OP_MID>(p, nullptr, S(stream)));
+    KL(1); CK(edm_launch<OP_MID>(p, nullptr, S(stream)));
     return ADB_OK;
 }
 
@@ -189,7 +201,7 @@ extern "C" int adb_edm_heun_post(const float* x, const float* d, const float* f2
     const PrecondCoef c = precond_coef(sigma1, sigma_data, sd2_of(sigma_data));
     EdmArgs p = edm_args(x, f2, nullptr, x_next, nullptr, n, n);
     p.s1 = sigma1; p.h = h; p.hh = 0.5f * h; p.c_skip1 = c.c_skip; p.c_out1 = c.c_out;
-    CK(edm_launch<OP_POST>(p, d, S(stream)));
+    KL(1); CK(edm_launch<OP_POST>(p, d, S(stream)));
     return ADB_OK;
 }
 
@@ -198,8 +210,9 @@ extern "C" int adb_edm_noise_in(const float* x, const float* noise, const float*
     REQUIRE(x && noise && sigmas && x_noisy && net_in && B > 0 && n_per > 0, "adb_edm_noise_in: bad arguments");
     EdmArgs p = edm_args(x, noise, nullptr, x_noisy, net_in, n_per, n_per * B);
     p.sigmas = sigmas; p.sigma_stride = 1; p.sigma_data = sigma_data; p.sd2 = sd2_of(sigma_data);
-    CK(edm_launch<OP_NOISE_IN>(p, nullptr, S(stream)));
+    KL(1); CK(edm_launch<OP_NOISE_IN>(p, nullptr, S(stream)));
     if (c_noise) {
+        KL(1);
         edm_cnoise_kernel<<<(B + 255) / 256, 256, 0, S(stream)>>>(sigmas, 1, c_noise, B);
         CK(cudaGetLastError());
     }
@@ -213,6 +226,7 @@ extern "C" int adb_edm_dsm_loss(const float* x, const float* x_noisy, const floa
     int chunks = static_cast<int>((n_per + 8191) / 8192);
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
+    KL(1);
     edm_dsm_loss_kernel<<<B * chunks, 256, 0, S(stream)>>>(x, x_noisy, f, sigmas, sigma_data, sd2_of(sigma_data), loss,
                                                            n_per, chunks);
     CK(cudaGetLastError());
@@ -941,7 +955,7 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
                 // x_hat = x + a * (s_noise * eps_i), each product rounded like the reference (:346-347)
                 EdmArgs p = edm_args(x, eps + static_cast<long long>(i) * N, nullptr, x, nullptr, N, N);
                 p.a = a; p.w0 = s_noise;
-                CK(edm_launch<OP_CHURN>(p, nullptr, st));
+                KL(1); CK(edm_launch<OP_CHURN>(p, nullptr, st));
             }
             rc = net_eval(n, x, sigma_hat, sigma_data, w.fbuf, B, L, precision, w, st);
             if (rc) return rc;
@@ -954,7 +968,7 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
                 {
                     ScopedTimer t(n, ADB_TIMER_STEP, st);
                     p.out0 = w.dslope; p.out1 = w.xnext;
-                    CK(edm_launch<OP_MID>(p, nullptr, st));
+                    KL(1); CK(edm_launch<OP_MID>(p, nullptr, st));
                 }
                 rc = net_eval(n, w.xnext, sigma_next, sigma_data, w.fbuf, B, L, precision, w, st);
                 if (rc) return rc;
@@ -963,11 +977,11 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
                 ScopedTimer t(n, ADB_TIMER_STEP, st);
                 p.out0 = x; p.out1 = nullptr;
                 p.s1 = sigma_next; p.hh = 0.5f * h; p.c_skip1 = c1.c_skip; p.c_out1 = c1.c_out;
-                CK(edm_launch<OP_POST>(p, w.dslope, st));
+                KL(1); CK(edm_launch<OP_POST>(p, w.dslope, st));
             } else {
                 ScopedTimer t(n, ADB_TIMER_STEP, st);
                 p.out0 = x;
-                CK(edm_launch<OP_EULER_RAW>(p, nullptr, st));
+                KL(1); CK(edm_launch<OP_EULER_RAW>(p, nullptr, st));
             }
         }
     } else {
@@ -988,7 +1002,7 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
                     ScopedTimer t(n, ADB_TIMER_STEP, st);
                     p.h = ah;                                                  // x_p = x + alpha h d   (:270)
                     p.out0 = w.dslope; p.out1 = w.xnext;
-                    CK(edm_launch<OP_MID>(p, nullptr, st));
+                    KL(1); CK(edm_launch<OP_MID>(p, nullptr, st));
                 }
                 rc = net_eval(n, w.xnext, sigma_p, sigma_data, w.fbuf, B, L, precision, w, st);
                 if (rc) return rc;
@@ -999,12 +1013,12 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
                 p.out0 = x; p.out1 = nullptr;
                 p.s1 = sigma_p; p.a = h; p.c_skip1 = c1.c_skip; p.c_out1 = c1.c_out;
                 p.w0 = static_cast<float>(1.0 - 0.5 / alpha); p.w1 = static_cast<float>(0.5 / alpha);
-                CK(edm_launch<OP_POST_RK2>(p, w.dslope, st));
+                KL(1); CK(edm_launch<OP_POST_RK2>(p, w.dslope, st));
             } else {
                 ScopedTimer t(n, ADB_TIMER_STEP, st);
                 p.h = h;
                 p.out0 = x;
-                CK(edm_launch<OP_EULER_RAW>(p, nullptr, st));
+                KL(1); CK(edm_launch<OP_EULER_RAW>(p, nullptr, st));
             }
         }
     }

@@ -190,7 +190,7 @@ def run_unet(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or 8
+    B = args.batch or 32
     torch.manual_seed(0)
     net = UNet1dBase(precision=args.precision, **UNET_CFG4)
     net.unet.to_out.to_out.weight.data.uniform_(-0.06, 0.06)          # zero-initialised in the reference (unet1d.py:619)
@@ -240,7 +240,9 @@ def run_unet(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
+    l0 = _native.lib().adb_launch_count(0) + net.graph_launches
     ms_res = timed(step_resident, args.steps)
+    launches = _native.lib().adb_launch_count(0) + net.graph_launches - l0
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
     _native.check_async()
@@ -258,7 +260,7 @@ def run_unet(args, rank, world, local_rank):
                            "l2": "CUDA-graph replay of ~400 launches per evaluation; activations of the upper levels exceed L2"},
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": noise_host.numel() * 4,
                         "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": None, "effective_tflops": UNET_FLOP_EVAL * nfe * total / (ms_res * 1e-3) / 1e12,
+                "gpu_launches": int(launches), "effective_tflops": UNET_FLOP_EVAL * nfe * total / (ms_res * 1e-3) / 1e12,
                 "ms_per_network_evaluation": ms_res / args.steps / nfe, "clocks": clk}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -325,7 +327,10 @@ def run_train(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
+    net.set_timing(False)                                  # zero the handle's launch counters
+    l0 = _native.lib().adb_launch_count(0)
     ms_res = timed(step_resident, args.steps)
+    launches = _native.lib().adb_launch_count(0) - l0 + sum(v[1] for v in net.timers().values())
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
     _native.check_async()
@@ -342,7 +347,7 @@ def run_train(args, rank, world, local_rank):
                            "l2": "saved activations (0.3 GB bf16 / 1.7 GB fp32 per sample) >> 126 MB L2"},
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + sig_host.numel() * 4,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": None, "effective_tflops": flop_step * args.steps / (ms_res * 1e-3) / 1e12, "clocks": clk}
+                "gpu_launches": int(launches), "effective_tflops": flop_step * args.steps / (ms_res * 1e-3) / 1e12, "clocks": clk}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -354,7 +359,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 8 UNet1d)")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 32 UNet1d / 16 train)")
     ap.add_argument("--workload", default="diffwave", choices=["diffwave", "unet1d", "train"],
                     help="diffwave = the headline metric (BASELINE.json configs[1]); unet1d = configs[3]")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])

@@ -37,6 +37,9 @@ int adb_version(void);
 int adb_device_check(int device);
 /* Synchronise the device and report any asynchronous kernel / pipeline error (test & bench use). */
 int adb_check_async(void);
+/* Kernel launches issued so far by the op-level entry points (adb_edm_*, adb_cl_*, training step) on this process;
+ * reset != 0 zeroes the counter. The DiffWave handle's own launches are reported by adb_wavenet_timers. */
+long long adb_launch_count(int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * EDM preconditioning — src/models/components/diffusion.py:232-241 (get_scale_weights) and :46-63
