@@ -197,3 +197,66 @@ class EDMAlphaSampler(nn.Module):
         for i in range(self.num_steps - 1):
             x = self.step(x, fn=fn, net=net, sigma=sig[i], sigma_next=sig[i + 1], **kwargs)
         return x
+
+
+class DPM2MSampler(nn.Module):
+    """DPM-Solver++(2M) Karras, deterministic multistep — sampler_edm.py:1056-1131.
+
+    Same constructor and `forward(noise, fn, net, sigmas)`; `sigmas` needs `num_steps + 1` entries (the reference
+    indexes `sigmas[i + 1]`, :1124), the last of which may be 0. Per step one denoiser call and ONE fused kernel
+    (`adb_edm_lincomb`: x <- a x - e (c0 D - c1 D_old)); the step scalars (t = -ln sigma, h, expm1) are computed on the
+    host from the schedule, so the loop never synchronises with the device.
+    """
+
+    def __init__(self, num_steps: int = 50, cond_scale: float = 1.0):
+        super().__init__()
+        self.num_steps = num_steps
+        self.cond_scale = cond_scale
+        self.last_nfe = 0
+
+    @staticmethod
+    def _coefficients(sigma_last: Optional[float], sigma: float, sigma_next: float, have_old: bool):
+        """(a, e, c0, c1) of x_next = a x - e (c0 D - c1 D_old) — sampler_edm.py:1089-1108, evaluated in fp32 like
+        the reference's 0-dim fp32 tensors (np.float32 arithmetic rounds after every operation)."""
+        import numpy as np
+        f = np.float32
+        with np.errstate(divide="ignore", over="ignore"):
+            t, t_next = -np.log(f(sigma)), -np.log(f(sigma_next))           # t_fn, :1082
+            h = f(t_next - t)
+            s_t, s_next = np.exp(-t), np.exp(-t_next)                        # sigma_fn, :1081
+            a = f(min(s_next, s_t) / max(s_next, s_t))                       # t_min / t_max, :1092-1093
+            if not have_old or sigma_next == 0:
+                return float(a), float(np.expm1(f(-h))), 1.0, 0.0           # :1097-1098
+            h_last = f(t - (-np.log(f(sigma_last))))
+            h_min, h_max = min(h_last, h), max(h_last, h)
+            r = f(h_max / h_min)
+            h_d = f(f(h_max + h_min) / f(2))
+            c0 = f(f(1) + f(f(1) / f(f(2) * r)))
+            c1 = f(f(1) / f(f(2) * r))
+            return float(a), float(np.expm1(f(-h_d))), float(c0), float(c1)
+
+    @torch.no_grad()
+    def forward(self, noise: Tensor, fn: Callable, net: nn.Module, sigmas: Tensor, **kwargs) -> Tensor:
+        noise = N.require_cuda_f32(noise, "noise")
+        N.ensure_device(noise.device)
+        sig = _host_sigmas(sigmas)
+        if len(sig) < self.num_steps + 1:
+            raise IndexError(f"schedule has {len(sig)} sigmas but DPM2MSampler indexes sigmas[{self.num_steps}] "
+                             "(sampler_edm.py:1124)")
+        lib, st, n = N.lib(), N.stream_ptr(noise.device), noise.numel()
+        self.last_nfe = 0
+        x = torch.empty_like(noise)
+        N.check(lib.adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), n, st))           # :1114
+        old = None
+        for i in range(self.num_steps):
+            den = N.require_cuda_f32(fn(x, net=net, sigma=sig[i], inference=True, cond_scale=self.cond_scale, **kwargs),
+                                     "denoised")
+            self.last_nfe += 1
+            a, e, c0, c1 = self._coefficients(sig[i - 1] if i > 0 else None, sig[i], sig[i + 1], old is not None)
+            second = old is not None and sig[i + 1] != 0
+            nxt = torch.empty_like(x)
+            N.check(lib.adb_edm_lincomb(N.ptr(x), N.ptr(den), N.ptr(old) if second else N.ptr(None), a, e, c0, c1, N.ptr(nxt), n, st))
+            x, old = nxt, den
+        out = torch.empty_like(x)
+        N.check(lib.adb_edm_clamp(N.ptr(x), N.ptr(out), n, st))                      # :1131
+        return out

@@ -185,6 +185,32 @@ extern "C" int adb_edm_rk2(const float* x, const float* d, const float* x1, cons
     return ADB_OK;
 }
 
+extern "C" int adb_edm_lincomb(const float* x, const float* d, const float* d_old, float a, float e, float c0, float c1,
+                               float* out, int64_t n, void* stream) {
+    REQUIRE(x && d && out && n > 0, "adb_edm_lincomb: bad arguments");
+    EdmArgs p = edm_args(x, d, d_old, out, nullptr, n, n);
+    p.a = a; p.s0 = e; p.w0 = c0; p.w1 = c1;
+    KL(1);
+    if (d_old) CK(edm_launch<OP_LINCOMB3>(p, nullptr, S(stream)));
+    else       CK(edm_launch<OP_LINCOMB2>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
+extern "C" int adb_edm_clamp(const float* x, float* out, int64_t n, void* stream) {
+    REQUIRE(x && out && n > 0, "adb_edm_clamp: bad arguments");
+    EdmArgs p = edm_args(x, nullptr, nullptr, out, nullptr, n, n);
+    KL(1); CK(edm_launch<OP_CLAMP>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
+extern "C" int adb_ema_lerp(float* ema, const float* params, float weight, int64_t n, void* stream) {
+    REQUIRE(ema && params && n > 0, "adb_ema_lerp: bad arguments");
+    EdmArgs p = edm_args(ema, params, nullptr, ema, nullptr, n, n);
+    p.a = weight;
+    KL(1); CK(edm_launch<OP_LERP>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
 extern "C" int adb_edm_heun_mid(const float* x, const float* f1, float sigma, float sigma_data, float h, float* d, float* x1,
                                 int64_t n, void* stream) {
     REQUIRE(x && f1 && d && x1 && n > 0, "adb_edm_heun_mid: bad arguments");

@@ -66,6 +66,10 @@ enum EdmOp : int {
     OP_NOISE_IN = 11,    // training: out0 = x + sigma_b * noise ; out1 = c_in(sigma_b) * out0   (diffusion.py:79,50/57)
     OP_SCALE = 12,       // out0 = a * x                                          (sampler_edm.py:380)
     OP_POST_RK2 = 13,    // fused general RK2: x' = x + h d; D2; out0 = x + a (w0 d + w1 d2)   (sampler_edm.py:270-278)
+    OP_LINCOMB2 = 14,    // out0 = a x - s0 in1                                   (DPM-Solver++(2M) 1st-order step, sampler_edm.py:1098)
+    OP_LINCOMB3 = 15,    // out0 = a x - s0 (w0 in1 - w1 in2)                     (2nd-order multistep, sampler_edm.py:1107-1108)
+    OP_CLAMP = 16,       // out0 = clamp(x, -1, 1)                                (sampler_edm.py:1131)
+    OP_LERP = 17,        // out0 = torch.lerp(x, in1, a)                          (EMA update, src/models/phema.py:107, :151)
 };
 
 struct EdmArgs {
@@ -101,8 +105,8 @@ __global__ void __launch_bounds__(256) edm_kernel(EdmArgs p, const float* __rest
             cs = c.c_skip; co = c.c_out; ci = c.c_in;
         }
         float x[VEC], i1[VEC], i2[VEC], i3[VEC], o0[VEC], o1[VEC];
-        constexpr bool need1 = (OP != OP_SCALE_IN && OP != OP_SCALE);
-        constexpr bool need2 = (OP == OP_COMBINE_CFG || OP == OP_HEUN || OP == OP_RK2);
+        constexpr bool need1 = (OP != OP_SCALE_IN && OP != OP_SCALE && OP != OP_CLAMP);
+        constexpr bool need2 = (OP == OP_COMBINE_CFG || OP == OP_HEUN || OP == OP_RK2 || OP == OP_LINCOMB3);
         constexpr bool need3 = (OP == OP_HEUN || OP == OP_RK2 || OP == OP_POST || OP == OP_POST_RK2);
         constexpr bool two_out = (OP == OP_EULER || OP == OP_MID || OP == OP_NOISE_IN);
         if constexpr (VEC == 4) {
@@ -168,6 +172,17 @@ __global__ void __launch_bounds__(256) edm_kernel(EdmArgs p, const float* __rest
                 o1[k] = __fadd_rn(x[k], __fmul_rn(p.h, d));
             } else if constexpr (OP == OP_SCALE) {
                 o0[k] = __fmul_rn(p.a, x[k]);
+            } else if constexpr (OP == OP_LINCOMB2) {
+                o0[k] = __fsub_rn(__fmul_rn(p.a, x[k]), __fmul_rn(p.s0, i1[k]));
+            } else if constexpr (OP == OP_LINCOMB3) {
+                const float dd = __fsub_rn(__fmul_rn(p.w0, i1[k]), __fmul_rn(p.w1, i2[k]));
+                o0[k] = __fsub_rn(__fmul_rn(p.a, x[k]), __fmul_rn(p.s0, dd));
+            } else if constexpr (OP == OP_CLAMP) {
+                o0[k] = clamp1(x[k]);
+            } else if constexpr (OP == OP_LERP) {
+                // torch.lerp: weight < 0.5 ? a + w (b - a) : b - (b - a) (1 - w)
+                const float diff = __fsub_rn(i1[k], x[k]);
+                o0[k] = p.a < 0.5f ? __fmaf_rn(p.a, diff, x[k]) : __fsub_rn(i1[k], __fmul_rn(diff, __fsub_rn(1.0f, p.a)));
             }
         }
         if constexpr (VEC == 4) {

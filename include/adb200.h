@@ -72,6 +72,16 @@ int adb_edm_euler(const float* x_dev, const float* denoised_dev, float sigma, fl
 int adb_edm_rk2(const float* x_dev, const float* d_dev, const float* x1_dev, const float* denoised1_dev,
                 float sigma1, float h, float w0, float w1, float* out_dev, int64_t n, void* stream);
 
+/* out = a x - e d                       (d_old_dev == NULL: DPM-Solver++(2M) first-order step, sampler_edm.py:1097-1098)
+ * out = a x - e (c0 d - c1 d_old)       (second-order multistep, sampler_edm.py:1100-1108) */
+int adb_edm_lincomb(const float* x_dev, const float* d_dev, const float* d_old_dev, float a, float e, float c0, float c1,
+                    float* out_dev, int64_t n, void* stream);
+/* out = clamp(x, -1, 1)                 (the final x.clamp of DPM2MSampler.forward, sampler_edm.py:1131) */
+int adb_edm_clamp(const float* x_dev, float* out_dev, int64_t n, void* stream);
+/* ema = torch.lerp(ema, params, weight) on flat vectors, in place — PowerFunctionEMA.update / TraditionalEMA.update
+ * (src/models/phema.py:104-108, :145-151), one launch per EMA instead of one per parameter tensor */
+int adb_ema_lerp(float* ema_dev, const float* params_dev, float weight, int64_t n, void* stream);
+
 /* Fused Heun step around RAW network outputs F (what the fused trajectory launches between network
  * evaluations; sampler_edm.py:350-367 with diffusion.py:60-63 inlined):
  *   mid : D1 = clamp(c_skip(s) x + c_out(s) F1) ; d = (x - D1)/s ; x1 = x + h d        reads 8 B, writes 8 B / element

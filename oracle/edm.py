@@ -137,3 +137,33 @@ def edm_alpha_sampler(noise, denoise_fn, sigmas, num_steps, alpha=1.0, use_heun=
     if trace is not None:
         trace.append(nfe)
     return x
+
+
+def dpm2m_sampler(noise, denoise_fn, sigmas, num_steps, trace=None):
+    """DPM2MSampler.forward / step — sampler_edm.py:1056-1131 (DPM-Solver++(2M) Karras). sigmas needs num_steps + 1
+    entries. denoise_fn(x, sigma) -> x0 estimate."""
+    sigma_fn = lambda t: t.neg().exp()                # noqa: E731
+    t_fn = lambda s: s.log().neg()                    # noqa: E731
+    x = sigmas[0] * noise
+    old = None
+    nfe = 0
+    for i in range(num_steps):
+        s_last, s, s_next = sigmas[i - 1], sigmas[i], sigmas[i + 1]
+        den = denoise_fn(x, s)
+        nfe += 1
+        t, t_next = t_fn(s), t_fn(s_next)
+        h = t_next - t
+        t_min, t_max = min(sigma_fn(t_next), sigma_fn(t)), max(sigma_fn(t_next), sigma_fn(t))
+        if old is None or s_next == 0:
+            x = (t_min / t_max) * x - (-h).expm1() * den
+        else:
+            h_last = t - t_fn(s_last)
+            h_min, h_max = min(h_last, h), max(h_last, h)
+            r = h_max / h_min
+            h_d = (h_max + h_min) / 2
+            den_d = (1 + 1 / (2 * r)) * den - (1 / (2 * r)) * old
+            x = (t_min / t_max) * x - (-h_d).expm1() * den_d
+        old = den
+    if trace is not None:
+        trace.append(nfe)
+    return x.clamp(-1.0, 1.0)
