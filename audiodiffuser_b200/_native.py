@@ -78,6 +78,9 @@ _SIGS = {
                                          c_void_p, c_int64, c_void_p]),
     "adb_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float,
                                c_int, c_float, c_void_p]),
+    "adb_cl_wavdec_packed_elems": (c_int64, [c_int]),
+    "adb_cl_wavdec_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_wavdec_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_wavenet_set_timing": (c_int, [c_void_p, c_int]),
     "adb_wavenet_timers": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
 }

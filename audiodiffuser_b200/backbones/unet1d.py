@@ -277,6 +277,12 @@ class UNet1dBase(nn.Module):
                 transformer(p + ".transformer")
             P[p + ".upsample"] = conv_k(p + ".upsample.weight", p + ".upsample.bias") if f == 1 else \
                 up(p + ".upsample.weight", p + ".upsample.bias", f)
+        nf, W, S = cfg["num_filters"], cfg["window_length"], cfg["stride"]
+        cout_w = cfg.get("out_channels") or cfg["in_channels"]
+        if bf16 and nf % 64 == 0 and W == 2 * S and S * cout_w <= 64:       # WAVdec on the tensor cores
+            pk = torch.empty(lib.adb_cl_wavdec_packed_elems(nf), dtype=torch.bfloat16, device=dev)
+            N.check(lib.adb_cl_wavdec_pack(N.ptr(P["to_out.to_out.weight"]), N.ptr(pk), nf, cout_w, W, S, st))
+            P["to_out.packed"] = pk
         P["cond_w"] = torch.cat(cond_w, dim=0).contiguous()
         P["cond_b"] = torch.cat(cond_b, dim=0).contiguous()
         P["cond_off"] = cond_off
@@ -403,7 +409,10 @@ class UNet1dBase(nn.Module):
         cout = cfg.get("out_channels") or cin
         if out.shape != (B, cout, (h.shape[1] - 1) * S - 2 * pad + W):
             raise N.AdbError(f"output buffer shape {tuple(out.shape)} does not match the network output")
-        N.check(lib.adb_cl_wavdec(N.ptr(h), N.ptr(P["to_out.to_out.weight"]), N.ptr(out), B, h.shape[1], nf, cout, W, S, dt, st))
+        if "to_out.packed" in P:
+            N.check(lib.adb_cl_wavdec_tc(N.ptr(h), N.ptr(P["to_out.packed"]), N.ptr(out), B, h.shape[1], nf, cout, W, S, st))
+        else:
+            N.check(lib.adb_cl_wavdec(N.ptr(h), N.ptr(P["to_out.to_out.weight"]), N.ptr(out), B, h.shape[1], nf, cout, W, S, dt, st))
         return out
 
     @torch.no_grad()

@@ -140,6 +140,23 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                 for (int i = 0; i < 32; ++i) v[i] = cl_act_fast(__uint_as_float(r[i]) + s_bias[cc * 32 + i], a.act);
                 long long o;
                 bool ok = row_ok;
+                if (a.cf_cout > 0) {
+                    // WAVdec: columns [0, ups * cf_cout) of this row are output samples t*ups + phase - shift of cf_cout
+                    // channels, written to the fp32 channels-first waveform (unet1d.py:596-622)
+                    if (ok && n < a.ups * a.cf_cout) {
+                        float* y = static_cast<float*>(a.out);
+                        const int ncols = a.ups * a.cf_cout - n;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < ncols) {
+                                const int col = n + i, ph = col / a.cf_cout, c = col % a.cf_cout;
+                                const int to = t * a.ups + ph - a.shift;
+                                if (to >= 0 && to < a.L_out) y[(static_cast<long long>(b) * a.cf_cout + c) * a.L_out + to] = v[i];
+                            }
+                        }
+                    }
+                    continue;
+                }
                 if (a.ups == 0) {
                     o = (static_cast<long long>(b) * a.rows + t) * a.N + n;
                     if (res && ok) {
@@ -179,6 +196,23 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// WAVdec1d filter bank [F][Cout][W = 2S] (torch ConvTranspose1d layout) -> the packed B operand of the 2-tap
+// GEMM-convolution Y[i][phase*Cout + c] = sum_f h[i][f] w[f][c][phase] + h[i-1][f] w[f][c][phase + S], N padded to 64
+__global__ void cl_pack_wavdec_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int F, int Cout, int W, int S) {
+    const int kbt = F / 64;
+    const int total = 2 * kbt * 64 * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i & 63, n = (i >> 6) & 63, kb = i >> 12;
+        const int tap = kb / kbt, f = (kb % kbt) * 64 + k;
+        float v = 0.f;
+        if (n < S * Cout) {
+            const int ph = n / Cout, c = n % Cout;
+            v = w[(static_cast<long long>(f) * Cout + c) * W + ph + tap * S];
+        }
+        out[i] = __float2bfloat16_rn(v);
     }
 }
 

@@ -62,6 +62,8 @@ struct ClConvArgs {
     int B, L_in, rows, Cin, N, taps, off0, dil, act;
     int ups;             // 0: normal store ; f > 0: transposed store with N = f * Cout
     int shift, L_out;    // transposed store: output row = t * ups + n / Cout - shift, kept if in [0, L_out)
+    int cf_cout;         // > 0 (tensor-core path only): WAVdec store — the first ups * cf_cout columns of row t hold the output
+                         // samples t * ups + phase - shift of cf_cout channels; out is fp32 channels-FIRST [B][cf_cout][L_out]
 };
 
 // fp32 tiled GEMM: 64 (rows) x 64 (n) x 16 (k), 256 threads, 4x4 outputs per thread. Cin % 16 == 0, N % 64 == 0.
@@ -608,6 +610,107 @@ __global__ void __launch_bounds__(256) cl_wavdec_smem_kernel(const T* __restrict
             acc = fmaf(h1[f], w0[f * Cout * W + S], acc);
         }
         y[(static_cast<long long>(b) * Cout + c) * L + T0 + tt] = acc;
+    }
+}
+
+// 16-byte vectorised concat (Ca, Cb multiples of the vector width; rows * (Ca + Cb) / VE < 2^31)
+template <typename T>
+__global__ void __launch_bounds__(256) cl_concat_vec_kernel(const T* __restrict__ a, const T* __restrict__ bsrc, float scale_b,
+                                                            T* __restrict__ out, unsigned rows, int Ca, int Cb) {
+    constexpr int VE = ClVec<T>::N;
+    const unsigned va = Ca / VE, vt = (Ca + Cb) / VE;
+    const unsigned total = rows * vt;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / vt, v = i - r * vt;
+        float x[VE];
+        if (v < va) {
+            ClVec<T>::load(a + (static_cast<size_t>(r) * va + v) * VE, x);
+        } else {
+            ClVec<T>::load(bsrc + (static_cast<size_t>(r) * (vt - va) + (v - va)) * VE, x);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) x[k] *= scale_b;
+        }
+        ClVec<T>::store(out + static_cast<size_t>(i) * VE, x);
+    }
+}
+
+// Batched small dense layer with the weights read ONCE for the whole batch: out[b][n] = act(bias[n] + sum_k W[n][k] f(in[b][k])).
+// The (optionally SiLU'd) inputs of up to 32 samples sit transposed in shared memory; lane = sample, one warp per output
+// column, weight rows loaded coalesced and broadcast with shuffles. grid (ceil(N / 8), ceil(B / 32)), smem = K * 32 floats.
+__global__ void __launch_bounds__(256) cl_linear_batched_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ out, int B, int K,
+                                                                int N, int silu_in, int act) {
+    extern __shared__ float xs[];                   // [K][32]
+    const int b0 = blockIdx.y * 32;
+    const int nb = min(32, B - b0);
+    for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+        const int k = i >> 5, bb = i & 31;
+        float v = 0.f;
+        if (bb < nb) {
+            v = in[static_cast<long long>(b0 + bb) * K + k];
+            if (silu_in) v = v / (1.0f + expf(-v));
+        }
+        xs[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    const float* wr = w + static_cast<long long>(n) * K;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const float wv = (k0 + lane < K) ? wr[k0 + lane] : 0.f;
+        const int kn = min(32, K - k0);
+        for (int j = 0; j < kn; ++j) acc = fmaf(__shfl_sync(0xffffffffu, wv, j), xs[(k0 + j) * 32 + lane], acc);
+    }
+    if (lane < nb) out[static_cast<long long>(b0 + lane) * N + n] = cl_act(acc + (bias ? bias[n] : 0.f), act);
+}
+
+// WAVenc1d, register-tiled: thread = 4 consecutive output rows x 4 consecutive filters; per (channel, tap) one 16-byte
+// weight load and four input loads feed 16 FMAs. Same staging as cl_wavenc_smem_kernel. F % 4 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256) cl_wavenc_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ out,
+                                                              int Cin, int L, int Lc, int F, int W, int S, int pad) {
+    extern __shared__ float sm_enc[];
+    constexpr int TT = 128;
+    float* ws = sm_enc;                       // [Cin*W][F]
+    const int span = TT * S + W;
+    float* xs = ws + Cin * W * F;             // [Cin][span]
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    for (int i = threadIdx.x; i < Cin * W * F; i += blockDim.x) {
+        const int f = i % F, ck = i / F;
+        ws[i] = w[static_cast<long long>(f) * Cin * W + ck];
+    }
+    for (int i = threadIdx.x; i < Cin * span; i += blockDim.x) {
+        const int c = i / span, j = i % span;
+        const int s = t0 * S - pad + j;
+        xs[i] = (s >= 0 && s < L) ? x[(static_cast<long long>(b) * Cin + c) * L + s] : 0.f;
+    }
+    __syncthreads();
+    const int f4n = F / 4;
+    for (int i = threadIdx.x; i < (TT / 4) * f4n; i += blockDim.x) {
+        const int r0 = (i / f4n) * 4, f0 = (i % f4n) * 4;
+        float acc[4][4] = {};
+        for (int c = 0; c < Cin; ++c) {
+            const float* xr = xs + c * span + r0 * S;
+            const float* wr = ws + c * W * F + f0;
+            for (int k = 0; k < W; ++k) {
+                const float4 wv = *reinterpret_cast<const float4*>(wr + k * F);
+                const float xv[4] = {xr[k], xr[S + k], xr[2 * S + k], xr[3 * S + k]};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc[u][0] = fmaf(wv.x, xv[u], acc[u][0]); acc[u][1] = fmaf(wv.y, xv[u], acc[u][1]);
+                    acc[u][2] = fmaf(wv.z, xv[u], acc[u][2]); acc[u][3] = fmaf(wv.w, xv[u], acc[u][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (t0 + r0 + u >= Lc) break;
+            T* o = out + (static_cast<long long>(b) * Lc + t0 + r0 + u) * F + f0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cl_st<T>(o + q, acc[u][q]);
+        }
     }
 }
 

@@ -352,7 +352,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                         const int c = lane & 3;                    // 16-byte chunk of the 64-byte row segment
                         const uint4 v = *reinterpret_cast<const uint4*>(tbuf + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4));
                         const int tt = t0 + q * 32 + rr;
-                        if (tile_valid && tt < p.L && !(p.dbg & 1))
+                        if (tile_valid && tt < p.L && !(p.dbg & 17))
                             *reinterpret_cast<uint4*>(p.h_out + (static_cast<long long>(b) * p.L + tt) * TC_C + col + c * 8) = v;
                     }
                 }
@@ -393,7 +393,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && tile_valid && !(p.dbg & 1)) {
+                    if (lane == 0 && tile_valid && !(p.dbg & 33)) {
                         if (p.first_layer) tma_store_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
                         else               tma_reduce_add_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
                         tma_store_commit();

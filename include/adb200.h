@@ -219,6 +219,13 @@ int adb_cl_wavenc(const float* x_dev, const float* w_dev, void* out_dev, int B, 
                   void* stream);
 int adb_cl_wavdec(const void* h_dev, const float* w_dev, float* y_dev, int B, int Lc, int F, int Cout, int W, int S, int dtype,
                   void* stream);
+/* WAVdec1d on the tensor cores for bf16 activations (F % 64 == 0, W == 2 S, S * Cout <= 64): the filter bank is packed once
+ * (adb_cl_wavdec_packed_elems(F) bf16 elements) and the transposed conv runs as a 2-tap GEMM-convolution with a
+ * channels-first fp32 store. */
+int64_t adb_cl_wavdec_packed_elems(int F);
+int adb_cl_wavdec_pack(const float* w_dev, void* packed_bf16_dev, int F, int Cout, int W, int S, void* stream);
+int adb_cl_wavdec_tc(const void* h_bf16_dev, const void* packed_bf16_dev, float* y_dev, int B, int Lc, int F, int Cout, int W,
+                     int S, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training step — Diffusion.forward (src/models/components/diffusion.py:65-97) through WaveNetNoise with the
