@@ -262,6 +262,27 @@ def run_unet(args, rank, world, local_rank):
                         "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "effective_tflops": UNET_FLOP_EVAL * nfe * total / (ms_res * 1e-3) / 1e12,
                 "ms_per_network_evaluation": ms_res / args.steps / nfe, "clocks": clk}
+        peaks = load_peaks()
+        line["roofline"] = {"bound": "tensor", "kernel": "whole network evaluation (cl_conv_tc_kernel is 46 % of it, profiles/r1_launches_unet1d_b32.csv)",
+                            "achieved": line["effective_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": line["effective_tflops"] / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"]}
+        if not args.no_cpu_baseline:
+            from oracle import unet1d as ounet
+            from oracle.weights import make_unet1d_state_dict
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+            sd_cpu = make_unet1d_state_dict(UNET_CFG4, 0)
+            xc, tc = torch.randn(1, 2, UNET_L), torch.zeros(1)
+            ts = []
+            with torch.no_grad():
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ounet.unet1d_forward(sd_cpu, UNET_CFG4, xc, tc)
+                    ts.append(time.perf_counter() - t0)
+            t_eval = sum(ts[1:]) / 2
+            line["cpu_baseline"] = {"value": 1.0 / (nfe * t_eval), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"B=1 x 2 full-size network evaluations after 1 warm-up (of {nfe} per waveform), fp32 torch-CPU "
+                                              f"oracle port, extrapolated x{nfe}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -348,6 +369,23 @@ def run_train(args, rank, world, local_rank):
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + sig_host.numel() * 4,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "effective_tflops": flop_step * args.steps / (ms_res * 1e-3) / 1e12, "clocks": clk}
+        peaks = load_peaks()
+        line["roofline"] = {"bound": "tensor", "kernel": "whole training step (forward pair kernel + cl_conv_tc dgrad + wgrad_tc + element-wise; "
+                                                          "3 x 606 GFLOP per sample)",
+                            "achieved": line["effective_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": line["effective_tflops"] / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"]}
+        if not args.no_cpu_baseline:
+            from oracle import edm as oedm, wavenet as owav
+            from oracle.weights import make_wavenet_state_dict
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+            sd_cpu = {k: v.requires_grad_(True) for k, v in make_wavenet_state_dict(C, LAYERS, seed=0).items()}
+            xc = (torch.randn(1, 1, L) * SIGMA_DATA).clamp(-1, 1)
+            t0 = time.perf_counter()
+            oedm.dsm_loss(xc, torch.randn(1, 1, L), torch.tensor([0.5]), owav.make_net_fn(sd_cpu, CYCLE), SIGMA_DATA).mean().backward()
+            t_step = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / t_step, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "one full-size B=1 forward + backward (autograd) of the fp32 torch-CPU oracle port, no optimizer"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
