@@ -286,7 +286,8 @@ struct LayerW {
     // transposed / tap-reversed copies for the data-gradient convolutions (training step)
     float *w2T, *w1d;
     // the same three matrices packed for cl_conv_tc_kernel (bf16 training step): forward recompute, dz, dx
-    __nv_bfloat16 *w1p, *w2Tp, *w1dp;
+    __nv_bfloat16 *w1p, *w2Tp, *w1dp;     // w1p: columns permuted to [128 gate | 128 filter] per 256-wide tile (CL_MODE_GATE_FWD)
+    float* b1p;                           // conv bias in the same column order
 };
 
 struct TimerPair {
@@ -312,6 +313,7 @@ struct adb_wavenet {
     float* d_scale = nullptr;         // g / ||v|| per weight-normed conv: [0] input, [1 + 2l] dilated, [2 + 2l] output, [last] skip
     WnJob* d_jobs = nullptr;
     float* wpT = nullptr;             // [512][C] scratch of refold
+    float* w1perm = nullptr;          // [3][C][2C] scratch of refold (column-permuted W1)
     std::vector<int64_t> counts, dst_off;   // flat-vector pieces (state_dict order) and their offsets in `params`
     const float** d_wp = nullptr;     // device arrays of per-layer pointers
     const float** d_bp = nullptr;
@@ -475,7 +477,8 @@ static int refold(adb_wavenet* n) {
         for (int l = 0; l < layers; ++l) {
             LayerW& w = n->L[l];
             pack_tc_layer_kernel<<<148 * 4, 256>>>(w.w1f, w.w2f, n->wtc + static_cast<size_t>(l) * 32 * 256 * 64);
-            cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1f, w.w1p, C, 2 * C, 3);
+            permute_gate_cols_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1f, w.b1, n->w1perm, w.b1p, 3 * C, C);
+            cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(n->w1perm, w.w1p, C, 2 * C, 3);
             cl_pack_conv_tc_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2T, w.w2Tp, 2 * C, C, 1);
             cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1d, w.w1dp, 2 * C, C, 3);
             transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, n->wpT, C, 512);     // [C][512] -> [512][C] (stream-ordered reuse)
@@ -584,6 +587,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     CKN(dmalloc(n, &n->wsp_f, static_cast<size_t>(C) * C));
     CKN(dmalloc(n, &n->wspT, static_cast<size_t>(C) * C));
     CKN(dmalloc(n, &n->wpT, 512ULL * C));
+    CKN(dmalloc(n, &n->w1perm, 3ULL * C * 2 * C));
     std::vector<const float*> h_wp(layers), h_bp(layers);
     for (int l = 0; l < layers; ++l) {
         LayerW& w = n->L[l];
@@ -592,7 +596,9 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(dmalloc(n, &w.w2T, 2ULL * C * C));
         CKN(dmalloc(n, &w.w1d, 3ULL * 2 * C * C));
         w.w1p = w.w2Tp = w.w1dp = nullptr;
+        w.b1p = nullptr;
         if (C == TC_C) {
+            CKN(dmalloc(n, &w.b1p, 2ULL * C));
             CKN(dmalloc(n, &w.w1p, 3ULL * C * 2 * C));
             CKN(dmalloc(n, &w.w2Tp, 2ULL * C * C));
             CKN(dmalloc(n, &w.w1dp, 3ULL * 2 * C * C));

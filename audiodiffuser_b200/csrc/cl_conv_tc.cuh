@@ -130,6 +130,77 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             mbar_wait(&bar_tfull[buf], use & 1, SITE_CT_TFULL, buf);
             tc_fence_after_sync();
             const bool row_ok = t < a.rows;
+            const long long grow = static_cast<long long>(b) * a.rows + t;      // global row
+            if (a.mode == CL_MODE_GATE_FWD) {
+                // tile = [128 gate | 128 filter] of channels 128 tn .. 128 tn + 127
+                const int C = a.N / 2;
+                __nv_bfloat16* yout = static_cast<__nv_bfloat16*>(a.aux_out);
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t rg[32], rf[32];
+                    tmem_ld_32x32(t_lane + buf * 256 + cc * 32, rg);
+                    tmem_ld_32x32(t_lane + buf * 256 + 128 + cc * 32, rf);
+                    tmem_ld_wait();
+                    const int c0 = 128 * tn + cc * 32;
+                    uint32_t pg[16], pf[16], pz[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float g0 = __uint_as_float(rg[i]) + s_bias[cc * 32 + i], g1 = __uint_as_float(rg[i + 1]) + s_bias[cc * 32 + i + 1];
+                        const float f0 = __uint_as_float(rf[i]) + s_bias[128 + cc * 32 + i], f1 = __uint_as_float(rf[i + 1]) + s_bias[128 + cc * 32 + i + 1];
+                        pg[i >> 1] = pack_bf16x2(g0, g1);
+                        pf[i >> 1] = pack_bf16x2(f0, f1);
+                        pz[i >> 1] = pack_bf16x2(__fdividef(1.0f, 1.0f + __expf(-g0)) * tanh_fast(f0),
+                                                 __fdividef(1.0f, 1.0f + __expf(-g1)) * tanh_fast(f1));
+                    }
+                    if (row_ok) {
+                        uint4* yg = reinterpret_cast<uint4*>(yout + grow * a.N + c0);
+                        uint4* yf = reinterpret_cast<uint4*>(yout + grow * a.N + C + c0);
+                        uint4* zo = reinterpret_cast<uint4*>(out + grow * C + c0);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            yg[m] = make_uint4(pg[4 * m], pg[4 * m + 1], pg[4 * m + 2], pg[4 * m + 3]);
+                            yf[m] = make_uint4(pf[4 * m], pf[4 * m + 1], pf[4 * m + 2], pf[4 * m + 3]);
+                            zo[m] = make_uint4(pz[4 * m], pz[4 * m + 1], pz[4 * m + 2], pz[4 * m + 3]);
+                        }
+                    }
+                }
+            } else if (a.mode == CL_MODE_GATE_BWD) {
+                const int C = a.N;
+                const __nv_bfloat16* yin = static_cast<const __nv_bfloat16*>(a.aux_in);
+                for (int cc = 0; cc < p.NT / 32; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_lane + buf * 256 + cc * 32, r);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    const int n = n0 + cc * 32;
+                    const uint4* ygp = reinterpret_cast<const uint4*>(yin + grow * 2 * C + n);
+                    const uint4* yfp = reinterpret_cast<const uint4*>(yin + grow * 2 * C + C + n);
+                    uint4* dg = reinterpret_cast<uint4*>(out + grow * 2 * C + n);
+                    uint4* df = reinterpret_cast<uint4*>(out + grow * 2 * C + C + n);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const uint4 ug = ygp[m], uf = yfp[m];
+                        const uint32_t wg[4] = {ug.x, ug.y, ug.z, ug.w}, wf[4] = {uf.x, uf.y, uf.z, uf.w};
+                        uint32_t og[4], of[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float dgv[2], dfv[2];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const float g = __uint_as_float(h ? (wg[e] & 0xFFFF0000u) : (wg[e] << 16));
+                                const float f = __uint_as_float(h ? (wf[e] & 0xFFFF0000u) : (wf[e] << 16));
+                                const float d = __uint_as_float(r[8 * m + 2 * e + h]);
+                                const float sg = __fdividef(1.0f, 1.0f + __expf(-g)), th = tanh_fast(f);
+                                dgv[h] = d * th * sg * (1.0f - sg);
+                                dfv[h] = d * sg * (1.0f - th * th);
+                            }
+                            og[e] = pack_bf16x2(dgv[0], dgv[1]);
+                            of[e] = pack_bf16x2(dfv[0], dfv[1]);
+                        }
+                        dg[m] = make_uint4(og[0], og[1], og[2], og[3]);
+                        df[m] = make_uint4(of[0], of[1], of[2], of[3]);
+                    }
+                }
+            } else
             for (int cc = 0; cc < p.NT / 32; ++cc) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_lane + buf * 256 + cc * 32, r);
@@ -158,9 +229,9 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                     continue;
                 }
                 if (a.ups == 0) {
-                    o = (static_cast<long long>(b) * a.rows + t) * a.N + n;
+                    o = grow * (a.ldo ? a.ldo : a.N) + n;
                     if (res && ok) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res + o);
+                        const uint4* rp = reinterpret_cast<const uint4*>(res + grow * (a.res_ld ? a.res_ld : a.N) + n);
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
                             const uint4 u = rp[m];
@@ -171,6 +242,10 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                                 v[8 * m + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
                             }
                         }
+                    }
+                    if (a.out_scale != 0.f) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= a.out_scale;
                     }
                 } else {
                     const int cout = a.N / a.ups, ph = n / cout, c = n % cout;

@@ -64,7 +64,19 @@ struct ClConvArgs {
     int shift, L_out;    // transposed store: output row = t * ups + n / Cout - shift, kept if in [0, L_out)
     int cf_cout;         // > 0 (tensor-core path only): WAVdec store — the first ups * cf_cout columns of row t hold the output
                          // samples t * ups + phase - shift of cf_cout channels; out is fp32 channels-FIRST [B][cf_cout][L_out]
+    // tensor-core path only (training step fusions); zero-initialised = plain behaviour
+    int mode;            // CL_MODE_PLAIN / CL_MODE_GATE_FWD / CL_MODE_GATE_BWD
+    long long ldo;       // row pitch of out (0: N)
+    long long res_ld;    // row pitch of res (0: N)
+    float out_scale;     // plain mode: out = (act(acc + bias) + res) * out_scale (0 is read as 1)
+    const void* aux_in;  // GATE_BWD: pre-gate activations y [B][rows][2N]
+    void* aux_out;       // GATE_FWD: pre-gate activations y [B][rows][N] (out receives z [B][rows][N/2])
 };
+// GATE_FWD: the N = 2C columns arrive permuted so that every 256-wide tile holds [128 gate | 128 filter] of the same 128
+//   channels (weights / bias packed that way): writes y in the ORIGINAL layout (gate c at column c, filter c at C + c) to
+//   aux_out and z = sigmoid(gate) tanh(filter) to out   (wavenet.py:110-112).
+// GATE_BWD: acc = dz [N = C]; reads y from aux_in and writes dy = [dz tanh(f) s (1 - s) | dz s (1 - tanh(f)^2)] to out [2C].
+enum ClMode : int { CL_MODE_PLAIN = 0, CL_MODE_GATE_FWD = 3, CL_MODE_GATE_BWD = 4 };
 
 // fp32 tiled GEMM: 64 (rows) x 64 (n) x 16 (k), 256 threads, 4x4 outputs per thread. Cin % 16 == 0, N % 64 == 0.
 __global__ void __launch_bounds__(256) cl_conv_f32_kernel(ClConvArgs p) {

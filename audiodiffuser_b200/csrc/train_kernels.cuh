@@ -127,6 +127,22 @@ __global__ void __launch_bounds__(256) axpby_kernel(const T* __restrict__ x, flo
     }
 }
 
+// Column permutation for CL_MODE_GATE_FWD: column n' of every 256-wide tile j holds gate channel 128 j + r (r = n' % 256 < 128)
+// or filter channel 128 j + r - 128; out[row][n'] = in[row][perm(n')], bias likewise. in: [rows][2C].
+__global__ void permute_gate_cols_kernel(const float* __restrict__ in, const float* __restrict__ bias_in, float* __restrict__ out,
+                                         float* __restrict__ bias_out, int rows, int C) {
+    const long long total = static_cast<long long>(rows) * 2 * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int np = static_cast<int>(i % (2 * C));
+        const long long row = i / (2 * C);
+        const int j = np >> 8, r = np & 255;
+        const int nsrc = r < 128 ? 128 * j + r : C + 128 * j + (r - 128);
+        out[i] = in[row * 2 * C + nsrc];
+        if (row == 0) bias_out[np] = bias_in[nsrc];
+    }
+}
+
 // dst (bf16) = src (fp32)
 __global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -194,7 +210,7 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const float* __restrict_
 // 16-byte channel vector and strides over the rows of its chunk. C <= 1024, 256 % (C / VE) == 0.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, float* __restrict__ out, int L, int C,
-                                                     int chunks, int per_sample) {
+                                                     int chunks, int per_sample, int ld) {
     constexpr int VE = ClVec<T>::N;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int rows_per = (L + chunks - 1) / chunks;
@@ -207,10 +223,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, f
     float s[VE];
 #pragma unroll
     for (int k = 0; k < VE; ++k) s[k] = 0.f;
-    const T* col = in + static_cast<size_t>(b) * L * C + v * VE;
+    const T* col = in + static_cast<size_t>(b) * L * ld + v * VE;     // ld = row pitch (>= C)
     for (int r = r0 + rofs; r < r1; r += rstep) {
         float x[VE];
-        ClVec<T>::load(col + static_cast<size_t>(r) * C, x);
+        ClVec<T>::load(col + static_cast<size_t>(r) * ld, x);
 #pragma unroll
         for (int k = 0; k < VE; ++k) s[k] += x[k];
     }
@@ -257,7 +273,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) inproj_bwd_kernel(const T* __restrict__ dh0, const T* __restrict__ h0,
                                                          const float* __restrict__ x, const float* __restrict__ scale,
                                                          float* __restrict__ dw_in, float* __restrict__ db_in, int L,
-                                                         long long rows, int C) {
+                                                         long long rows, int C, int ld_dh, float dh_scale) {
     __shared__ float aw[1024], ab[1024];
     for (int c = threadIdx.x; c < C; c += blockDim.x) { aw[c] = 0.f; ab[c] = 0.f; }
     __syncthreads();
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(256) inproj_bwd_kernel(const T* __restrict__ d
     const int rstep = blockDim.x / C, rofs = threadIdx.x / C;
     float lw = 0.f, lb = 0.f;
     for (long long r = static_cast<long long>(blockIdx.x) * rstep + rofs; r < rows; r += static_cast<long long>(gridDim.x) * rstep) {
-        const float m = cl_ld<T>(h0 + r * C + c) > 0.f ? cl_ld<T>(dh0 + r * C + c) : 0.f;
+        const float m = cl_ld<T>(h0 + r * C + c) > 0.f ? cl_ld<T>(dh0 + r * ld_dh + c) * dh_scale : 0.f;
         const float xv = __fmul_rn(scale[r / L], x[r]);
         lw = fmaf(m, xv, lw);
         lb += m;
@@ -322,6 +338,27 @@ __global__ void __launch_bounds__(512) embproj_bwd_kernel(const float* __restric
         float acc = 0.f;
         for (int c = 0; c < C; ++c) acc = fmaf(dpl[b * C + c], w[static_cast<long long>(c) * 512 + k], acc);
         atomicAdd(demb + b * 512 + k, acc);
+    }
+}
+
+// bf16 backward bookkeeping: with U_l = (gradient wrt the output of block l) / sqrt(2) and S[l + 1] = per-sample column sums
+// of U_l (S[0]: of U_{-1} = grad wrt the first block's input / sqrt(2)):
+//   db2_l[0:C] = sum_b S[l+1][b] ; db2_l[C:2C] = column sums of dskip ; dp_l[b] = colsum_b(dx_l) = sqrt(2) S[l][b] - S[l+1][b]
+// grid (layers), C threads.
+__global__ void train_finalize_kernel(const float* __restrict__ S /*[layers+1][B][C]*/, const float* __restrict__ dbskip,
+                                      float* __restrict__ grad_layers, long long layer_stride, long long b2_off,
+                                      float* __restrict__ dp /*[layers][B][C]*/, int B, int C) {
+    const int l = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float tot = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const float s1 = S[(static_cast<long long>(l + 1) * B + b) * C + c];
+            tot += s1;
+            dp[(static_cast<long long>(l) * B + b) * C + c] = 1.41421356237309505f * S[(static_cast<long long>(l) * B + b) * C + c] - s1;
+        }
+        float* b2 = grad_layers + l * layer_stride + b2_off;
+        b2[c] = tot;
+        b2[C + c] = dbskip[c];
     }
 }
 
