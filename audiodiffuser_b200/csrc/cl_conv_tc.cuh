@@ -21,8 +21,21 @@ constexpr int CT_STAGES = 4;
 constexpr int CT_A_BYTES = 128 * 64 * 2;            // 16 KB
 constexpr int CT_B_BYTES = 256 * 64 * 2;            // 32 KB (NT = 256; smaller tiles use a prefix)
 constexpr int CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
-constexpr int CT_THREADS = 192;                     // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int CT_THREADS = 192;                     // plain instantiation: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 1024 /*bias*/ + 16 * 8 + 16;
+
+// Activation applied to a 32-column register chunk with the activation as a COMPILE-TIME constant: the switch is taken once
+// per chunk, never per element (left to the optimiser, a per-element uniform branch on the runtime value can survive the
+// unrolling and costs 30 % of the small-K convolutions).
+template <int ACT>
+__device__ __forceinline__ void ct_act32(float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if constexpr (ACT == CL_ACT_RELU) v[i] = fmaxf(v[i], 0.f);
+        else if constexpr (ACT == CL_ACT_SILU) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
+        else if constexpr (ACT == CL_ACT_GELU) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+    }
+}
 
 enum CtWaitSite : uint32_t { SITE_CT_EMPTY = 20, SITE_CT_FULL = 21, SITE_CT_TEMPTY = 22, SITE_CT_TFULL = 23 };
 
@@ -33,9 +46,13 @@ struct ClConvTcParams {
     int tiles_m;            // B * tiles_per_b
     int tiles_n;            // N / NT
     int kb_per_tap;         // Cin / 64
+    int epi_warps;          // 4 (block of 192 threads) or 8 (block of 320): the fused gate epilogues need the second set
 };
 
-__global__ void __launch_bounds__(CT_THREADS, 1)
+// EPI_WARPS = 4 (192 threads) for the plain / transposed / WAVdec stores; EPI_WARPS = 8 (320 threads) with FUSED = true adds
+// the training step's gate-forward / gate-derivative epilogues, which are epilogue-bound with four warps.
+template <int EPI_WARPS, bool FUSED>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const ClConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_bias = reinterpret_cast<float*>(smem + CT_STAGES * CT_STAGE_BYTES);
@@ -52,7 +69,7 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], EPI_WARPS); }
             fence_mbar_init();
         }
         __syncwarp();
@@ -111,6 +128,9 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         }
     } else {
         const int q = warp & 3;
+        constexpr int nhalf = EPI_WARPS >> 2;          // 1: this warp handles every column chunk ; 2: half of them
+        const int half = (warp - 2) >> 2;              // which half of the tile's column chunks this warp handles
+        constexpr int epi_threads = 32 * EPI_WARPS;
         const int row = q * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
@@ -122,20 +142,20 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             const int b = tm / p.tiles_per_b, t = (tm % p.tiles_per_b) * 128 + row, n0 = tn * p.NT;
             const uint32_t buf = it & 1, use = it >> 1;
             if (n0 != cur_n0) {                     // bias slice of this n-tile (epilogue warps only: named barrier 1)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = threadIdx.x - 64; i < p.NT; i += 128) s_bias[i] = a.bias ? a.bias[n0 + i] : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(epi_threads) : "memory");
+                for (int i = threadIdx.x - 64; i < p.NT; i += epi_threads) s_bias[i] = a.bias ? a.bias[n0 + i] : 0.f;
+                asm volatile("bar.sync 1, %0;" ::"n"(epi_threads) : "memory");
                 cur_n0 = n0;
             }
             mbar_wait(&bar_tfull[buf], use & 1, SITE_CT_TFULL, buf);
             tc_fence_after_sync();
             const bool row_ok = t < a.rows;
             const long long grow = static_cast<long long>(b) * a.rows + t;      // global row
-            if (a.mode == CL_MODE_GATE_FWD) {
+            if (FUSED && a.mode == CL_MODE_GATE_FWD) {
                 // tile = [128 gate | 128 filter] of channels 128 tn .. 128 tn + 127
                 const int C = a.N / 2;
                 __nv_bfloat16* yout = static_cast<__nv_bfloat16*>(a.aux_out);
-                for (int cc = 0; cc < 4; ++cc) {
+                for (int cc = (nhalf == 2 ? 2 * half : 0); cc < (nhalf == 2 ? 2 * half + 2 : 4); ++cc) {
                     uint32_t rg[32], rf[32];
                     tmem_ld_32x32(t_lane + buf * 256 + cc * 32, rg);
                     tmem_ld_32x32(t_lane + buf * 256 + 128 + cc * 32, rf);
@@ -163,10 +183,12 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                         }
                     }
                 }
-            } else if (a.mode == CL_MODE_GATE_BWD) {
+            } else if (FUSED && a.mode == CL_MODE_GATE_BWD) {
                 const int C = a.N;
                 const __nv_bfloat16* yin = static_cast<const __nv_bfloat16*>(a.aux_in);
-                for (int cc = 0; cc < p.NT / 32; ++cc) {
+                const int nch = p.NT / 32;
+                const int c_lo = nhalf == 2 ? half * ((nch + 1) / 2) : 0, c_hi = (nhalf == 2 && !half) ? (nch + 1) / 2 : nch;
+                for (int cc = c_lo; cc < c_hi; ++cc) {
                     uint32_t r[32];
                     tmem_ld_32x32(t_lane + buf * 256 + cc * 32, r);
                     tmem_ld_wait();
@@ -201,14 +223,20 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                     }
                 }
             } else
-            for (int cc = 0; cc < p.NT / 32; ++cc) {
+            for (int cc = (nhalf == 2 ? half * ((p.NT / 32 + 1) / 2) : 0); cc < ((nhalf == 2 && !half) ? (p.NT / 32 + 1) / 2 : p.NT / 32); ++cc) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_lane + buf * 256 + cc * 32, r);
                 tmem_ld_wait();
                 const int n = n0 + cc * 32;
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = cl_act_fast(__uint_as_float(r[i]) + s_bias[cc * 32 + i], a.act);
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + s_bias[cc * 32 + i];
+                switch (a.act) {
+                    case CL_ACT_RELU: ct_act32<CL_ACT_RELU>(v); break;
+                    case CL_ACT_SILU: ct_act32<CL_ACT_SILU>(v); break;
+                    case CL_ACT_GELU: ct_act32<CL_ACT_GELU>(v); break;
+                    default: break;
+                }
                 long long o;
                 bool ok = row_ok;
                 if (a.cf_cout > 0) {
