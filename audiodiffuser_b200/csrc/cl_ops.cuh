@@ -494,11 +494,12 @@ __global__ void __launch_bounds__(256) cl_gn_stats_vec_kernel(const T* __restric
 // GroupNorm apply: per-group mean / rstd are finished in fp64 by G threads, per-channel affine coefficients
 // (normalisation, gain / bias and the optional (scale + 1, shift) folded) are built once per block in shared memory,
 // then one vectorised fused pass. grid (chunks, B); C <= 2048, G <= 64.
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256) cl_gn_apply_vec_kernel(const T* __restrict__ in, const double* __restrict__ sums,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ ss, long long ss_ld, T* __restrict__ out,
-                                                              int L, int C, int G, float eps, int act, int chunks) {
+                                                              int L, int C, int G, float eps, int chunks) {
+    constexpr int act = ACT;                      // compile-time: no per-element switch
     constexpr int VE = ClVec<T>::N;
     __shared__ float ca[2048], cb[2048];
     __shared__ float s_mean[64], s_rstd[64];
