@@ -420,6 +420,17 @@ static int make_weight_map(CUtensorMap* map, const void* base, uint64_t rows, ui
 static int make_act_map(CUtensorMap* map, const void* base, int B, int L, int kind) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (kind == 4) {        // bf16 store map for the pair kernel's residual output: box [32 ch][32 t][1], 64-byte swizzle
+        cuuint64_t dims4[3] = {256, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+        cuuint64_t strides4[2] = {512, static_cast<cuuint64_t>(L) * 512};
+        cuuint32_t box4[3] = {32, 32, 1};
+        cuuint32_t estr4[3] = {1, 1, 1};
+        CUresult r4 = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims4, strides4, box4, estr4,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r4 != CUDA_SUCCESS) return fail(ADB_ERR_CUDA, "cuTensorMapEncodeTiled(act kind 4) failed: %d", static_cast<int>(r4));
+        return ADB_OK;
+    }
     const bool f32 = (kind == 2);
     const cuuint64_t esz = f32 ? 4 : 2;
     cuuint64_t dims[3] = {256, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
@@ -868,7 +879,10 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
             la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
             lc.attrs = la; lc.numAttrs = 1;
             bp.cluster = 2;
-            CK(cudaLaunchKernelEx(&lc, wavenet_block_pair_kernel, m_h, n->tm_w2, m_skip, bp));
+            CUtensorMap m_hout4;
+            rc = get_act_map(n, hout, B, L, 4, &m_hout4);
+            if (rc) return rc;
+            CK(cudaLaunchKernelEx(&lc, wavenet_block_pair_kernel, m_h, n->tm_w2, m_skip, m_hout4, bp));
         } else {
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3(grid_block); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = TC_BLOCK_SMEM_BYTES; lc.stream = st;

@@ -38,7 +38,8 @@ constexpr int TC2_SMEM_BYTES = Tc2Smem::total;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
-                          const __grid_constant__ CUtensorMap tm_skip, const BlockTcParams p) {
+                          const __grid_constant__ CUtensorMap tm_skip, const __grid_constant__ CUtensorMap tm_hout,
+                          const BlockTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_evec = reinterpret_cast<float*>(smem + Tc2Smem::evec);
     float* s_esum = reinterpret_cast<float*>(smem + Tc2Smem::esum);
@@ -60,6 +61,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
         tma_prefetch_desc(&tm_h);
         tma_prefetch_desc(&tm_w);
         tma_prefetch_desc(&tm_skip);
+        tma_prefetch_desc(&tm_hout);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -339,6 +341,23 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                         const float v0 = (__uint_as_float(r[i]) + s_b2[col + i]) * 0.70710678118654752f;
                         const float v1 = (__uint_as_float(r[i + 1]) + s_b2[col + i + 1]) * 0.70710678118654752f;
                         pk[i >> 1] = pack_bf16x2(v0, v1);
+                    }
+                    if (!(p.dbg & 64)) {
+                        // the 32 x 32-channel chunk leaves as ONE asynchronous TMA tensor store from this warp's 2 KB buffer
+                        // (rows of 64 bytes, 64-byte swizzle); rows past L are clipped by the hardware
+                        if (lane == 0) tma_store_wait_read<0>();       // previous chunk's store has read the buffer
+                        __syncwarp();
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((m ^ sw_w) << 4)) =
+                                make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && tile_valid && !(p.dbg & 17)) {
+                            tma_store_3d(&tm_hout, tbuf, col, t0 + q * 32, b);
+                            tma_store_commit();
+                        }
+                        continue;
                     }
                     __syncwarp();                                  // previous chunk fully read back
 #pragma unroll
