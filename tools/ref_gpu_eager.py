@@ -1,0 +1,47 @@
+"""Context number for BASELINE.json configs[4] ("vs reference PyTorch GPU ... paths"): the reference ALGORITHM (the oracle
+restatement, which is plain torch code and bit-identical to the reference's modules on CPU) run with PyTorch eager on the
+same B200 — fp32 and bf16 autocast — next to the fused path. Not part of bench.py; prints one JSON line per case.
+
+    python tools/ref_gpu_eager.py [B]
+"""
+import json, os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import edm as oedm, wavenet as owav
+from oracle.weights import make_wavenet_state_dict
+from audiodiffuser_b200 import WaveNetNoise, EluDiffusion, _native
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+C, LAYERS, CYCLE, L = 256, 36, 12, 16000
+dev = torch.device("cuda:0")
+sd = make_wavenet_state_dict(C, LAYERS, seed=0)
+sd_dev = {k: v.to(dev) for k, v in sd.items()}
+x = torch.randn(B, 1, L, device=dev)
+
+
+def timed(fn, reps=3):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps
+
+
+net_fn = owav.make_net_fn(sd_dev, CYCLE)
+with torch.no_grad():
+    t_fp32 = timed(lambda: oedm.denoise(x, net_fn, 0.2, sigma=1.0))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        t_bf16 = timed(lambda: oedm.denoise(x, net_fn, 0.2, sigma=1.0))
+net = WaveNetNoise(C, LAYERS, CYCLE, precision="bf16")
+net.load_state_dict(sd, strict=True)
+net = net.to(dev)
+diff = EluDiffusion(0.2)
+t_ours = timed(lambda: diff.denoise_fn(x, net=net, sigma=1.0, inference=True))
+_native.check_async()
+for name, t in (("torch eager fp32 (cuDNN)", t_fp32), ("torch eager bf16 autocast (cuDNN)", t_bf16), ("adb200 bf16 fused", t_ours)):
+    print(json.dumps({"case": name, "batch": B, "ms_per_denoiser_call": 1e3 * t, "samples_per_s_heun18": B / (35 * t),
+                      "tflops": 606.093e9 * B / t / 1e12}))
