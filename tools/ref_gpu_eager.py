@@ -18,6 +18,7 @@ dev = torch.device("cuda:0")
 sd = make_wavenet_state_dict(C, LAYERS, seed=0)
 sd_dev = {k: v.to(dev) for k, v in sd.items()}
 x = torch.randn(B, 1, L, device=dev)
+sig = torch.full((B,), 1.0, device=dev)
 
 
 def timed(fn, reps=3):
@@ -33,9 +34,9 @@ def timed(fn, reps=3):
 
 net_fn = owav.make_net_fn(sd_dev, CYCLE)
 with torch.no_grad():
-    t_fp32 = timed(lambda: oedm.denoise(x, net_fn, 0.2, sigma=1.0))
+    t_fp32 = timed(lambda: oedm.denoise(x, net_fn, 0.2, sigmas=sig))
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        t_bf16 = timed(lambda: oedm.denoise(x, net_fn, 0.2, sigma=1.0))
+        t_bf16 = timed(lambda: oedm.denoise(x, net_fn, 0.2, sigmas=sig))
 net = WaveNetNoise(C, LAYERS, CYCLE, precision="bf16")
 net.load_state_dict(sd, strict=True)
 net = net.to(dev)
