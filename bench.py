@@ -128,14 +128,17 @@ def step_kernel_hbm(dev, elements=64 * 1024 * 1024, reps=6):
             "avg_ms": ms / (2 * reps), "elements": elements}
 
 
+CPU_BATCH = 8        # BASELINE.json configs[0]: the reference's CPU-runnable case is batch 8
+
+
 def cpu_reference_eval_time(n_evals, threads):
-    """Time `n_evals` full-size network evaluations (B = 1) of the oracle port on the host."""
+    """Time `n_evals` full-size network evaluations (B = CPU_BATCH) of the oracle port on the host."""
     from oracle import edm as oedm, wavenet as owav
     from oracle.weights import make_wavenet_state_dict
     torch.set_num_threads(threads)
     sd = make_wavenet_state_dict(C, LAYERS, seed=0)
     net_fn = owav.make_net_fn(sd, CYCLE)
-    x = torch.randn(1, 1, L, generator=torch.Generator().manual_seed(1))
+    x = torch.randn(CPU_BATCH, 1, L, generator=torch.Generator().manual_seed(1))
     times = []
     with torch.no_grad():
         for s in ([80.0, 1.0, 0.05] * ((n_evals + 2) // 3))[:n_evals]:
@@ -154,8 +157,8 @@ def run_reference(args, rank, world):
         cpu_reference_eval_time(1, threads)
     t = cpu_reference_eval_time(evals_per_step * max(args.steps, 1), threads)
     t_eval = sum(t) / len(t)
-    value = 1.0 / (NFE * t_eval)                       # samples/s: one sample needs NFE evaluations
-    sample = (f"B=1 x {len(t)} full-size network evaluations (of the {NFE} one sample needs), fp32, "
+    value = CPU_BATCH / (NFE * t_eval)                 # samples/s: one sample needs NFE evaluations
+    sample = (f"B={CPU_BATCH} x {len(t)} full-size network evaluations (of the {NFE} one trajectory needs), fp32, "
               f"extrapolated x{NFE}; torch {torch.__version__} CPU, {threads} threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * evals_per_step * t_eval, "higher_is_better": True,
@@ -536,9 +539,9 @@ def main():
             threads = os.cpu_count() or 1
             t = cpu_reference_eval_time(4, threads)
             t_eval = sum(t[1:]) / len(t[1:])
-            line["cpu_baseline"] = {"value": 1.0 / (NFE * t_eval), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"B=1 x 3 full-size network evaluations after 1 warm-up (of {NFE} per sample), "
-                                              f"fp32 torch-CPU oracle port, extrapolated x{NFE}"}
+            line["cpu_baseline"] = {"value": CPU_BATCH / (NFE * t_eval), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"B={CPU_BATCH} x 3 full-size network evaluations after 1 warm-up (of {NFE} per trajectory, "
+                                              f"BASELINE.json configs[0] shape), fp32 torch-CPU oracle port, extrapolated x{NFE}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
