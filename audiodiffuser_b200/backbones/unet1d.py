@@ -30,10 +30,11 @@ def _param_shapes(cfg) -> "OrderedDict[str, tuple]":
     nf, W, cin = cfg["num_filters"], cfg["window_length"], cfg["in_channels"]
     cout = cfg.get("out_channels") or cin
     T, am, km = ch * 4, cfg["attention_multiplier"], cfg["kernel_multiplier_downsample"]
+    cdim = ch * 4 if cfg.get("class_cond") else 0                    # classes_channels, unet1d.py:843-850
     s = OrderedDict()
 
     def resnet(p, ci, co):
-        s[p + ".to_cond_embedding.1.weight"] = (2 * co, T)
+        s[p + ".to_cond_embedding.1.weight"] = (2 * co, T + cdim)
         s[p + ".to_cond_embedding.1.bias"] = (2 * co,)
         for blk, c_in in (("block1", ci), ("block2", co)):
             s[f"{p}.{blk}.groupnorm.weight"] = (c_in,)
@@ -132,9 +133,9 @@ class UNet1dBase(nn.Module):
                  text_cond_multiplier: int = None, use_self_text_cond: bool = False, use_condition_block: bool = False,
                  precision: str = "bf16", **kwargs):
         super().__init__()
-        if class_cond or text_cond or use_condition_block:
-            raise NotImplementedError("the fused UNet1d covers the unconditional configuration (SURVEY.md §8 a13); "
-                                      "class / text conditioning and the condition block are not built")
+        if text_cond or use_condition_block or (class_cond and num_classes is None):
+            raise NotImplementedError("the fused UNet1d covers the unconditional and the label-conditioned (num_classes) "
+                                      "configurations; text conditioning, class embeddings and the condition block are not built")
         if kwargs.get("use_nearest_upsample", False):
             raise NotImplementedError("use_nearest_upsample=True (nn.Upsample + ReflectionPad1d, unet1d.py:234-245) is not built")
         if precision not in N.PRECISIONS:
@@ -145,7 +146,7 @@ class UNet1dBase(nn.Module):
         missing = [k for k in required if k not in kwargs]
         if missing:
             raise TypeError(f"UNet1d missing required arguments: {missing}")       # like the reference's signature
-        cfg = dict(channels=channels, **kwargs)
+        cfg = dict(channels=channels, class_cond=bool(class_cond), num_classes=num_classes, **kwargs)
         n = len(cfg["multipliers"]) - 1
         assert len(cfg["factors"]) == n and len(cfg["attentions"]) == n and len(cfg["num_blocks"]) == n   # unet1d.py:672-675
         if cfg["num_filters"] != channels * cfg["multipliers"][0]:
@@ -155,6 +156,16 @@ class UNet1dBase(nn.Module):
         self.cfg = cfg
         self.cond_drop_prob = cond_drop_prob
         self.precision = precision
+        if class_cond:                                            # LabelEmbedder, conditioner.py:59-92 (registered before the unet)
+            cd = channels * 4
+            self.label_conditioner = _Node()
+            for name, v in (("null_classes_emb", torch.randn(1, channels)), ("label_emb.weight", torch.randn(num_classes, channels)),
+                            ("class_to_cond.0.weight", torch.ones(channels)), ("class_to_cond.0.bias", torch.zeros(channels)),
+                            ("class_to_cond.1.weight", (torch.rand(cd, channels) * 2 - 1) / math.sqrt(channels)),
+                            ("class_to_cond.1.bias", (torch.rand(cd) * 2 - 1) / math.sqrt(channels)),
+                            ("class_to_cond.3.weight", (torch.rand(cd, cd) * 2 - 1) / math.sqrt(cd)),
+                            ("class_to_cond.3.bias", (torch.rand(cd) * 2 - 1) / math.sqrt(cd))):
+                _register(self.label_conditioner, name, v)
         self.unet = _Node()
         shapes = _param_shapes(cfg)
         for name, shape in shapes.items():
@@ -178,7 +189,9 @@ class UNet1dBase(nn.Module):
         key = self._param_key()
         if self._packed is not None and key == self._packed_key:
             return self._packed
-        sd = {k[len("unet."):]: v.detach().to(torch.float32) for k, v in self.state_dict().items()}
+        sd = {k[len("unet."):]: v.detach().to(torch.float32) for k, v in self.state_dict().items() if k.startswith("unet.")}
+        lc = {k[len("label_conditioner."):]: v.detach().to(torch.float32).contiguous() for k, v in self.state_dict().items()
+              if k.startswith("label_conditioner.")}
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise N.AdbError("UNet1dBase parameters are on the CPU: adb200 has no CPU path; call .cuda() on a B200")
@@ -286,13 +299,14 @@ class UNet1dBase(nn.Module):
         P["cond_w"] = torch.cat(cond_w, dim=0).contiguous()
         P["cond_b"] = torch.cat(cond_b, dim=0).contiguous()
         P["cond_off"] = cond_off
+        P["lc"] = lc
         torch.cuda.current_stream(dev).synchronize()
         self._packed, self._packed_key = P, key
         self._graphs = {}
         return P
 
     # ---- one forward as a sequence of C-ABI calls -------------------------------------------------
-    def _run(self, x: Tensor, t: Tensor, out: Tensor):
+    def _run(self, x: Tensor, t: Tensor, out: Tensor, classes: Optional[Tensor] = None, drop: Optional[Tensor] = None):
         cfg, P = self.cfg, self._pack()
         lib, dev = N.lib(), x.device
         st = N.stream_ptr(dev)
@@ -364,9 +378,27 @@ class UNet1dBase(nn.Module):
         temb = torch.empty(B, T, dtype=torch.float32, device=dev)
         N.check(lib.adb_cl_linear(N.ptr(e1), N.ptr(P["to_time.2.weight"]), N.ptr(P["to_time.2.bias"]), N.ptr(temb), B, T, T, 0,
                                   ACT_NONE, st))
+        cond = temb
+        if classes is not None:                                   # LabelEmbedder.forward, conditioner.py:94-111 + unet1d.py:304-306
+            lc, ch = P["lc"], cfg["channels"]
+            cd = lc["class_to_cond.3.bias"].numel()
+            e0 = torch.empty(B, ch, dtype=torch.float32, device=dev)
+            N.check(lib.adb_cl_label_embed(N.ptr(lc["label_emb.weight"]), N.ptr(lc["null_classes_emb"]), N.ptr(classes), N.ptr(drop),
+                                           N.ptr(e0), B, ch, cfg["num_classes"], st))
+            e1 = torch.empty_like(e0)
+            N.check(lib.adb_cl_layernorm(N.ptr(e0), N.ptr(lc["class_to_cond.0.weight"]), N.ptr(lc["class_to_cond.0.bias"]), N.ptr(e1), B,
+                                         ch, 1e-5, 0, st))
+            e2 = torch.empty(B, cd, dtype=torch.float32, device=dev)
+            N.check(lib.adb_cl_linear(N.ptr(e1), N.ptr(lc["class_to_cond.1.weight"]), N.ptr(lc["class_to_cond.1.bias"]), N.ptr(e2), B, ch,
+                                      cd, 0, ACT_SILU, st))
+            e3 = torch.empty(B, cd, dtype=torch.float32, device=dev)
+            N.check(lib.adb_cl_linear(N.ptr(e2), N.ptr(lc["class_to_cond.3.weight"]), N.ptr(lc["class_to_cond.3.bias"]), N.ptr(e3), B, cd,
+                                      cd, 0, ACT_NONE, st))
+            cond = torch.empty(B, T + cd, dtype=torch.float32, device=dev)
+            N.check(lib.adb_cl_concat(N.ptr(temb), N.ptr(e3), 1.0, N.ptr(cond), B, T, cd, 0, st))
         ss_all = torch.empty(B, P["cond_w"].shape[0], dtype=torch.float32, device=dev)
-        N.check(lib.adb_cl_linear(N.ptr(temb), N.ptr(P["cond_w"]), N.ptr(P["cond_b"]), N.ptr(ss_all), B, T, ss_all.shape[1], 1,
-                                  ACT_NONE, st))
+        N.check(lib.adb_cl_linear(N.ptr(cond), N.ptr(P["cond_w"]), N.ptr(P["cond_b"]), N.ptr(ss_all), B, cond.shape[1], ss_all.shape[1],
+                                  1, ACT_NONE, st))
 
         # input transform (WAVenc1d, unet1d.py:572-594)
         nf = cfg["num_filters"]
@@ -420,39 +452,70 @@ class UNet1dBase(nn.Module):
                 text_mask: Optional[Tensor] = None, inj_embeddings: Optional[Tensor] = None,
                 inj_channels: Optional[Tensor] = None, cond_drop_prob=None, **kwargs) -> Tensor:
         """(x [B, in_channels, L], t [B]) -> [B, out_channels, L]   (unet1d.py:856-893)."""
-        if any(v is not None for v in (classes, text_embeds, inj_embeddings, inj_channels)):
-            raise NotImplementedError("conditioning inputs are outside the fused unconditional UNet1d")
+        if any(v is not None for v in (text_embeds, inj_embeddings, inj_channels)):
+            raise NotImplementedError("text / injection conditioning inputs are outside the fused UNet1d")
+        if classes is not None and not self.cfg["class_cond"]:
+            raise NotImplementedError("this UNet1d was built without class conditioning (class_cond=False)")
         x = N.require_cuda_f32(x, "x")
         if x.ndim != 3 or x.shape[1] != self.cfg["in_channels"]:
             raise N.AdbError(f"UNet1d expects x [B, {self.cfg['in_channels']}, L]; got {tuple(x.shape)}")
         B, _, L = x.shape
         t = N.require_cuda_f32(t, "t").reshape(B)
+        drop = None
+        if classes is not None:
+            p = self.cond_drop_prob if cond_drop_prob is None else cond_drop_prob
+            if isinstance(p, Tensor):                                # per-sample flags (used by the batched CFG pair)
+                drop = p.to(device=x.device, dtype=torch.int32).reshape(B).contiguous()
+            elif p <= 0:
+                drop = torch.zeros(B, dtype=torch.int32, device=x.device)
+            elif p >= 1:
+                drop = torch.ones(B, dtype=torch.int32, device=x.device)
+            else:
+                raise NotImplementedError("random label dropout (0 < cond_drop_prob < 1, training) is not built on the fused path")
+            classes = classes.to(device=x.device, dtype=torch.int64).reshape(B).contiguous()
         self._pack()
         cout = self.cfg.get("out_channels") or self.cfg["in_channels"]
         if not self.use_cuda_graph:
-            return self._run(x, t, torch.empty(B, cout, L, dtype=torch.float32, device=x.device))
-        # CUDA graph per (B, L): ~400 small launches per evaluation would otherwise be host-bound
-        key = (B, L, x.device.index)
+            return self._run(x, t, torch.empty(B, cout, L, dtype=torch.float32, device=x.device), classes, drop)
+        # CUDA graph per (B, L, conditioned): ~400 small launches per evaluation would otherwise be host-bound
+        key = (B, L, x.device.index, classes is not None)
         g = self._graphs.get(key)
         if g is None:
             sx, stt = torch.empty_like(x), torch.empty_like(t)
             so = torch.empty(B, cout, L, dtype=torch.float32, device=x.device)
+            sc = torch.zeros(B, dtype=torch.int64, device=x.device) if classes is not None else None
+            sdp = torch.zeros(B, dtype=torch.int32, device=x.device) if classes is not None else None
             sx.copy_(x)
             stt.copy_(t)
+            if sc is not None:
+                sc.copy_(classes)
+                sdp.copy_(drop)
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream(x.device))
             with torch.cuda.stream(side):
-                self._run(sx, stt, so)                          # warm-up outside capture (tensor-map cache, attributes)
+                self._run(sx, stt, so, sc, sdp)                 # warm-up outside capture (tensor-map cache, attributes)
             torch.cuda.current_stream(x.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             before = N.lib().adb_launch_count(0)
             with torch.cuda.graph(graph):
-                self._run(sx, stt, so)
+                self._run(sx, stt, so, sc, sdp)
             per_replay = N.lib().adb_launch_count(0) - before
-            g = self._graphs[key] = (graph, sx, stt, so, per_replay)
-        graph, sx, stt, so, per_replay = g
+            g = self._graphs[key] = (graph, sx, stt, so, per_replay, sc, sdp)
+        graph, sx, stt, so, per_replay, sc, sdp = g
         sx.copy_(x)
         stt.copy_(t)
+        if sc is not None:
+            sc.copy_(classes)
+            sdp.copy_(drop)
         graph.replay()
         self.graph_launches += per_replay
         return so.clone()
+
+    @torch.no_grad()
+    def _adb_cfg_pair(self, x: Tensor, t: Tensor, classes: Tensor):
+        """Classifier-free guidance pair in ONE network evaluation of batch 2B (diffusion.py:50-53 calls the net twice):
+        returns (F(x | classes), F(x | null))."""
+        B = x.shape[0]
+        flags = torch.cat([torch.zeros(B, dtype=torch.int32, device=x.device), torch.ones(B, dtype=torch.int32, device=x.device)])
+        out = self.forward(torch.cat([x, x]), torch.cat([t, t]), classes=torch.cat([classes, classes]), cond_drop_prob=flags)
+        return out[:B], out[B:]

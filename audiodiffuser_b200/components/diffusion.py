@@ -82,7 +82,11 @@ class EluDiffusion(Diffusion):
         N.check(lib.adb_edm_precond_in(N.ptr(x), N.ptr(sig), stride, float(self.sigma_data), N.ptr(net_in),
                                        N.ptr(c_noise), B, n_per, st))
         f_null = None
-        if inference:
+        pair = getattr(net, "_adb_cfg_pair", None)
+        if inference and cond_scale != 1.0 and pair is not None and set(kwargs) == {"classes"} and kwargs["classes"] is not None:
+            # both guidance branches in one batch-2B evaluation of the fused backbone (diffusion.py:50-53 calls it twice)
+            pred, f_null = pair(net_in, c_noise, kwargs["classes"])
+        elif inference:
             pred = net(net_in, c_noise, cond_drop_prob=0., **kwargs)
             if cond_scale != 1.0:
                 f_null = net(net_in, c_noise, cond_drop_prob=1., **kwargs)

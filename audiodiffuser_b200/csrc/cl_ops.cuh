@@ -171,6 +171,17 @@ __global__ void __launch_bounds__(256) cl_linear_kernel(const float* __restrict_
     if (lane == 0) out[warp] = cl_act(acc + (bias ? bias[n] : 0.f), act);
 }
 
+// LabelEmbedder lookup (conditioner.py:94-106): out[b] = drop[b] ? null_row : table[labels[b]]. One block per sample.
+__global__ void cl_label_embed_kernel(const float* __restrict__ table, const float* __restrict__ null_row,
+                                      const long long* __restrict__ labels, const int* __restrict__ drop, float* __restrict__ out,
+                                      int C, int num_classes) {
+    const int b = blockIdx.x;
+    const long long lab = labels[b];
+    const bool use_null = (drop && drop[b]) || lab < 0 || lab >= num_classes;
+    const float* src = use_null ? null_row : table + lab * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) out[static_cast<long long>(b) * C + c] = src[c];
+}
+
 // [t, sin(2 pi t w_j), cos(2 pi t w_j)]   (LearnedPositionalEmbedding, unet1d.py:128-142). out: [B][2*half + 1]
 __global__ void cl_time_features_kernel(const float* __restrict__ t, const float* __restrict__ w, float* __restrict__ out,
                                         int B, int half) {

@@ -197,6 +197,10 @@ int adb_cl_wgrad(const void* a_dev, const void* g_dev, float* out_dev, int B, in
  * to_cond_embedding :271-276, :304-308) */
 int adb_cl_linear(const float* in_dev, const float* w_dev, const float* bias_dev, float* out_dev, int B, int K, int N,
                   int silu_in, int act, void* stream);
+/* LabelEmbedder lookup with classifier-free-guidance dropout (conditioner.py:94-106): out[b] = drop[b] ? null_row :
+ * table[labels[b]] (labels int64 [B]; drop int32 [B] or NULL = keep all); fp32 [B][C] */
+int adb_cl_label_embed(const float* table_dev, const float* null_row_dev, const long long* labels_dev, const int* drop_dev,
+                       float* out_dev, int B, int C, int num_classes, void* stream);
 /* [t, sin(2 pi t w), cos(2 pi t w)] -> out [B][2*half+1]   (LearnedPositionalEmbedding, unet1d.py:128-142) */
 int adb_cl_time_features(const float* t_dev, const float* w_dev, float* out_dev, int B, int half, void* stream);
 /* nn.GroupNorm(G, C) + optional x*(scale+1)+shift (scale_shift_dev [B][ss_ld]: scale at [0,C), shift at [C,2C)) +

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle.ref_loader import import_reference                      # noqa: E402
 from oracle.make_golden import save, seeded                          # noqa: E402
 from oracle.weights import (make_unet1d_state_dict, unet1d_param_shapes, UNET1D_CONFIG4, UNET_SMALL, UNET_MID,   # noqa: E402
-                            UNET_CASES as CASES)
+                            UNET_CLASS, UNET_CASES as CASES)
 from oracle import unet1d as ounet                                   # noqa: E402
 
 def build_ref(R, cfg, seed):
@@ -53,6 +53,17 @@ def main():
                                      use_heun=True)
     res["heun"] = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig)
     save("unet1d_mid_edm", noise=noise, sigmas=sig, cfg=np.array([B, L, seed, steps], dtype=np.int64), **res)
+
+    # label conditioning + classifier-free guidance (conditioner.py:59-111, diffusion.py:50-54)
+    cfg, B, L, seed = UNET_CLASS, 2, 4096, 106
+    net, sd = build_ref(R, cfg, seed)
+    x = seeded((B, 2, L), seed + 1000)
+    t = seeded((B,), seed + 2000, 1.5)
+    cls = torch.tensor([3, 7])
+    res = {"f_cond": net(x, t, classes=cls, cond_drop_prob=0.0), "f_null": net(x, t, classes=cls, cond_drop_prob=1.0)}
+    for s_ in (10.0, 0.5):
+        res[f"den_cfg_sigma_{s_}"] = diff.denoise_fn(x * s_, net=net, sigma=torch.tensor(s_), inference=True, cond_scale=2.5, classes=cls)
+    save("unet1d_class_cfg", x=x, t=t, classes=cls, cfg=np.array([B, L, seed], dtype=np.int64), **res)
 
 
 if __name__ == "__main__":

@@ -44,8 +44,22 @@ def conv_block(sd, prefix, x, groups, scale_shift=None):
     return F.conv1d(x, _p(sd, prefix + ".project.weight"), _p(sd, prefix + ".project.bias"), padding=1)
 
 
+def label_embedding(sd, classes, cond_drop_prob):
+    """LabelEmbedder.forward for integer labels (conditioner.py:59-111): cond_drop_prob = 0 keeps every label, 1 replaces
+    every label by the learned null embedding (operator_utils.py:46-52); then LayerNorm -> Linear -> SiLU -> Linear."""
+    emb = F.embedding(classes, sd["label_conditioner.label_emb.weight"])
+    if cond_drop_prob >= 1:
+        emb = sd["label_conditioner.null_classes_emb"].expand_as(emb)
+    elif cond_drop_prob > 0:
+        raise NotImplementedError("random label dropout (training) is not restated")
+    C = emb.shape[-1]
+    h = F.layer_norm(emb, (C,), sd["label_conditioner.class_to_cond.0.weight"], sd["label_conditioner.class_to_cond.0.bias"], eps=1e-5)
+    h = F.silu(F.linear(h, sd["label_conditioner.class_to_cond.1.weight"], sd["label_conditioner.class_to_cond.1.bias"]))
+    return F.linear(h, sd["label_conditioner.class_to_cond.3.weight"], sd["label_conditioner.class_to_cond.3.bias"])
+
+
 def resnet_block(sd, prefix, x, temb, groups):
-    """ResnetBlock1d (unet1d.py:257-316)."""
+    """ResnetBlock1d (unet1d.py:257-316). `temb` is cat(time_embed, class_embed) when class-conditioned (:304-306)."""
     ce = F.linear(F.silu(temb), _p(sd, prefix + ".to_cond_embedding.1.weight"), _p(sd, prefix + ".to_cond_embedding.1.bias"))
     scale, shift = ce[:, :, None].chunk(2, dim=1)
     h = conv_block(sd, prefix + ".block1", x, groups)
@@ -90,8 +104,9 @@ def transformer_block(sd, prefix, x, heads):
     return h + x
 
 
-def unet1d_forward(sd, cfg, x, t):
-    """UNet1dBase.forward -> UNet1d.forward (unet1d.py:856-893, :769-816). x: [B, in_channels, L], t: [B]."""
+def unet1d_forward(sd, cfg, x, t, classes=None, cond_drop_prob=0.0):
+    """UNet1dBase.forward -> UNet1d.forward (unet1d.py:856-893, :769-816). x: [B, in_channels, L], t: [B];
+    classes: integer labels [B] when cfg["class_cond"] (unet1d.py:877)."""
     groups, heads = cfg["resnet_groups"], cfg["attention_heads"]
     factors, num_blocks, attentions = cfg["factors"], cfg["num_blocks"], cfg["attentions"]
     W, S = cfg["window_length"], cfg["stride"]
@@ -100,6 +115,8 @@ def unet1d_forward(sd, cfg, x, t):
 
     x = F.conv1d(x, _p(sd, "to_in.to_in.weight"), stride=S, padding=W // 2 - S // 2)
     temb = time_embedding(sd, t)
+    if classes is not None:
+        temb = torch.cat((temb, label_embedding(sd, classes, cond_drop_prob)), dim=-1)
     skips_list = []
     for i in range(n_levels):
         pre = f"downsamples.{i}"
@@ -140,4 +157,4 @@ def unet1d_forward(sd, cfg, x, t):
 
 def make_net_fn(sd, cfg):
     """net(x [B,C,L], c_noise [B], **kw) for oracle.edm.denoise (unconditional: kwargs ignored)."""
-    return lambda x, t, **kw: unet1d_forward(sd, cfg, x, t)
+    return lambda x, t, classes=None, cond_drop_prob=0.0, **kw: unet1d_forward(sd, cfg, x, t, classes, cond_drop_prob)

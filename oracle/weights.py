@@ -100,6 +100,7 @@ UNET_MID = dict(channels=64, cond_drop_prob=0.0, class_cond=False, text_cond=Fal
                 in_channels=2, resnet_groups=8, kernel_multiplier_downsample=2, multipliers=[1, 2, 4], factors=[4, 2],
                 num_blocks=[2, 1], attentions=[False, True], attention_heads=8, attention_multiplier=2,
                 use_nearest_upsample=False, use_skip_scale=True, use_attention_bottleneck=True)
+UNET_CLASS = dict(UNET_MID, class_cond=True, num_classes=10)     # label conditioning + classifier-free guidance
 UNET_CASES = {   # name: (cfg, B, L, seed)
     "unet1d_small": (UNET_SMALL, 2, 256, 101),
     "unet1d_small_ragged": (UNET_SMALL, 3, 96, 102),         # L/stride/f0/f1 = 3 rows at the bottom: tiles far from full
@@ -119,9 +120,20 @@ def unet1d_param_shapes(cfg):
     T = ch * 4
     am = cfg["attention_multiplier"]
     shapes = OrderedDict()
+    cdim = ch * 4 if cfg.get("class_cond") else 0           # classes_channels (unet1d.py:843-850)
+    if cfg.get("class_cond"):
+        assert cfg.get("num_classes") is not None, "only the label (num_classes) conditioner is restated"
+        shapes["label_conditioner.null_classes_emb"] = (1, ch)
+        shapes["label_conditioner.label_emb.weight"] = (cfg["num_classes"], ch)
+        shapes["label_conditioner.class_to_cond.0.weight"] = (ch,)
+        shapes["label_conditioner.class_to_cond.0.bias"] = (ch,)
+        shapes["label_conditioner.class_to_cond.1.weight"] = (cdim, ch)
+        shapes["label_conditioner.class_to_cond.1.bias"] = (cdim,)
+        shapes["label_conditioner.class_to_cond.3.weight"] = (cdim, cdim)
+        shapes["label_conditioner.class_to_cond.3.bias"] = (cdim,)
 
     def resnet(p, ci, co):
-        shapes[p + ".to_cond_embedding.1.weight"] = (2 * co, T)
+        shapes[p + ".to_cond_embedding.1.weight"] = (2 * co, T + cdim)
         shapes[p + ".to_cond_embedding.1.bias"] = (2 * co,)
         shapes[p + ".block1.groupnorm.weight"] = (ci,)
         shapes[p + ".block1.groupnorm.bias"] = (ci,)
@@ -195,8 +207,10 @@ def make_unet1d_state_dict(cfg, seed=0, dtype=torch.float32):
         return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
 
     for name, shape in unet1d_param_shapes(cfg).items():
-        if name.endswith("to_time.0.0.weights"):
+        if name.endswith("to_time.0.0.weights") or name.endswith("null_classes_emb") or name.endswith("label_emb.weight"):
             sd[name] = torch.randn(shape, generator=g, dtype=torch.float32)
+        elif name.endswith("class_to_cond.0.weight"):
+            sd[name] = 1.0 + uni(shape, 0.2)
         elif name.endswith(".g") or name.endswith("groupnorm.weight") or name.endswith("norm.weight"):
             sd[name] = 1.0 + uni(shape, 0.2)
         elif name.endswith(".bias"):

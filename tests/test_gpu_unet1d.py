@@ -88,7 +88,31 @@ def test_unet_rejects_conditioning(dev):
     from audiodiffuser_b200 import UNet1dBase
     from oracle.weights import UNET_SMALL
     with pytest.raises(NotImplementedError):
-        UNet1dBase(**dict(UNET_SMALL, class_cond=True, num_classes=10))
+        UNet1dBase(**dict(UNET_SMALL, text_cond=True))
     net = UNet1dBase(precision="fp32", **UNET_SMALL).to(dev)
     with pytest.raises(NotImplementedError):
         net(torch.zeros(1, 2, 256, device=dev), torch.zeros(1, device=dev), classes=torch.zeros(1, dtype=torch.long, device=dev))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_class_conditioning_and_cfg(dev, precision):
+    """Label conditioning (LabelEmbedder, conditioner.py:59-111) and classifier-free guidance through denoise_fn
+    (diffusion.py:50-54): the fused path evaluates both guidance branches as one batch-2B network call."""
+    from audiodiffuser_b200 import EluDiffusion, _native as N
+    from oracle.weights import UNET_CLASS
+    g = load_golden("unet1d_class_cfg")
+    B, L, seed = (int(v) for v in g["cfg"])
+    net = make_unet(UNET_CLASS, seed, precision, dev)
+    x, t, cls = (torch.from_numpy(g[k]).to(dev) for k in ("x", "t", "classes"))
+    for p, key in ((0.0, "f_cond"), (1.0, "f_null")):
+        e = rel_l2(net(x, t, classes=cls, cond_drop_prob=p), g[key])
+        assert e < TOL[precision], (precision, key, e)
+    diff = EluDiffusion(0.2)
+    for s in (10.0, 0.5):
+        out = diff.denoise_fn(x * s, net=net, sigma=s, inference=True, cond_scale=2.5, classes=cls)
+        e = rel_l2(out, g[f"den_cfg_sigma_{s}"])
+        print(f"class-conditioned CFG {precision} sigma={s}: rel-L2 {e:.3e}")
+        assert e < (1e-5 if precision == "fp32" else 3e-2), (precision, s, e)
+    N.check_async()
+    with pytest.raises(NotImplementedError):
+        net(x, t, classes=cls, cond_drop_prob=0.3)

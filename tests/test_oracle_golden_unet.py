@@ -40,3 +40,17 @@ def test_unet_edm_denoise_and_sampler_golden():
             assert rel_l2(edm.denoise(noise * s, net_fn, 0.2, sigma=s), g[f"den_sigma_{s}"]) < 1e-6
         x = edm.edm_sampler(noise, lambda x_, s_: edm.denoise(x_, net_fn, 0.2, sigma=float(s_)), torch.from_numpy(g["sigmas"]), steps)
     assert rel_l2(x, g["heun"]) < 1e-5
+
+
+def test_unet_class_conditioning_oracle_golden():
+    from oracle import edm, unet1d as ou
+    from oracle.weights import UNET_CLASS, make_unet1d_state_dict
+    g = load_golden("unet1d_class_cfg")
+    B, L, seed = (int(v) for v in g["cfg"])
+    sd = make_unet1d_state_dict(UNET_CLASS, seed)
+    x, t, cls = (torch.from_numpy(g[k]) for k in ("x", "t", "classes"))
+    with torch.no_grad():
+        assert rel_l2(ou.unet1d_forward(sd, UNET_CLASS, x, t, cls, 0.0), g["f_cond"]) < 1e-6
+        assert rel_l2(ou.unet1d_forward(sd, UNET_CLASS, x, t, cls, 1.0), g["f_null"]) < 1e-6
+        den = edm.denoise(x * 0.5, ou.make_net_fn(sd, UNET_CLASS), 0.2, sigma=0.5, cond_scale=2.5, classes=cls)
+    assert rel_l2(den, g["den_cfg_sigma_0.5"]) < 1e-6
