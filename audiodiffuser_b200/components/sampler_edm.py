@@ -260,3 +260,65 @@ class DPM2MSampler(nn.Module):
         out = torch.empty_like(x)
         N.check(lib.adb_edm_clamp(N.ptr(x), N.ptr(out), n, st))                      # :1131
         return out
+
+
+class ADPM2Sampler(nn.Module):
+    """Ancestral DPM-Solver-2 ('DPM2 a Karras') — stochastic_sampler_edm.py:30-100, the default sampler of the reference's
+    model config (configs/model/diffunet_complex.yaml:23). Same constructor and `forward(noise, fn, net, sigmas)`.
+
+    Two denoiser calls per step; the arithmetic around them is three fused kernels (adb_edm_euler, adb_edm_rk2 with
+    weights (0, 1), adb_edm_axpy for the ancestral noise) with step scalars computed on the host in fp32.
+    `eps` (optional, [num_steps - 1, *noise.shape]) fixes the ancestral noise for parity tests; by default one
+    `randn_like(x)` is drawn per step like stochastic_sampler_edm.py:80.
+    """
+
+    def __init__(self, rho: float = 1.0, num_steps: int = 50, cond_scale: float = 1.0, eta: float = 1.0):
+        super().__init__()
+        self.rho = rho
+        self.num_steps = num_steps
+        self.cond_scale = cond_scale
+        self.eta = eta
+        self.last_nfe = 0
+
+    def _sigmas(self, sigma: float, sigma_next: float):
+        """(sigma_up, sigma_down, sigma_mid) — get_sigmas (:30-33) and :69, in fp32 like the reference's 0-dim tensors."""
+        import numpy as np
+        f = np.float32
+        s, sn = f(sigma), f(sigma_next)
+        inner = f(f(sn ** 2) * f(f(s ** 2) - f(sn ** 2))) / f(s ** 2)
+        up = min(sn, f(f(self.eta) * f(np.sqrt(f(inner)))))
+        down = f(np.sqrt(f(f(sn ** 2) - f(up ** 2))))
+        inv = 1.0 / self.rho
+        mid = f(f(f(f(s ** f(inv)) + f(down ** f(inv))) / f(2)) ** f(self.rho))
+        return float(up), float(down), float(mid)
+
+    @torch.no_grad()
+    def forward(self, noise: Tensor, fn: Callable, net: nn.Module, sigmas: Tensor, eps: Optional[Tensor] = None,
+                **kwargs) -> Tensor:
+        noise = N.require_cuda_f32(noise, "noise")
+        N.ensure_device(noise.device)
+        sig = _host_sigmas(sigmas)
+        if len(sig) < self.num_steps:
+            raise IndexError(f"schedule has {len(sig)} sigmas but ADPM2Sampler indexes sigmas[{self.num_steps - 1}]")
+        lib, st, n = N.lib(), N.stream_ptr(noise.device), noise.numel()
+        self.last_nfe = 0
+        x = torch.empty_like(noise)
+        N.check(lib.adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), n, st))
+        for i in range(self.num_steps - 1):
+            sigma, sigma_next = sig[i], sig[i + 1]
+            up, down, mid = self._sigmas(sigma, sigma_next)
+            den = N.require_cuda_f32(fn(x, net=net, sigma=sigma, inference=True, cond_scale=self.cond_scale, **kwargs), "denoised")
+            d, x_mid = torch.empty_like(x), torch.empty_like(x)
+            N.check(lib.adb_edm_euler(N.ptr(x), N.ptr(den), sigma, _f32(mid - sigma), N.ptr(d), N.ptr(x_mid), n, st))        # :66-70
+            den_mid = N.require_cuda_f32(fn(x_mid, net=net, sigma=mid, inference=True, cond_scale=self.cond_scale, **kwargs),
+                                         "denoised")
+            self.last_nfe += 2
+            x_det = torch.empty_like(x)
+            N.check(lib.adb_edm_rk2(N.ptr(x), N.ptr(d), N.ptr(x_mid), N.ptr(den_mid), mid, _f32(down - sigma), 0.0, 1.0,
+                                    N.ptr(x_det), n, st))                                                                      # :76-78
+            e = eps[i] if eps is not None else torch.randn_like(x)
+            x = torch.empty_like(x_det)
+            N.check(lib.adb_edm_axpy(N.ptr(x_det), N.ptr(N.require_cuda_f32(e, "eps")), up, N.ptr(x), n, st))                 # :79
+        out = torch.empty_like(x)
+        N.check(lib.adb_edm_clamp(N.ptr(x), N.ptr(out), n, st))
+        return out

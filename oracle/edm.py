@@ -167,3 +167,22 @@ def dpm2m_sampler(noise, denoise_fn, sigmas, num_steps, trace=None):
     if trace is not None:
         trace.append(nfe)
     return x.clamp(-1.0, 1.0)
+
+
+def adpm2_sampler(noise, denoise_fn, sigmas, num_steps, rho=1.0, eta=1.0, eps_fn=None):
+    """ADPM2Sampler.forward / step — stochastic_sampler_edm.py:30-100 ('DPM2 a Karras', ancestral). eps_fn(x) supplies the
+    ancestral noise (default torch.randn_like, one draw per step)."""
+    if eps_fn is None:
+        eps_fn = torch.randn_like
+    x = sigmas[0] * noise
+    for i in range(num_steps - 1):
+        s, s_next = sigmas[i], sigmas[i + 1]
+        s_up = min(s_next, eta * (s_next ** 2 * (s ** 2 - s_next ** 2) / s ** 2) ** 0.5)
+        s_down = (s_next ** 2 - s_up ** 2) ** 0.5
+        d = (x - denoise_fn(x, s)) / s
+        s_mid = ((s ** (1 / rho) + s_down ** (1 / rho)) / 2) ** rho
+        x_mid = x + d * (s_mid - s)
+        d_mid = (x_mid - denoise_fn(x_mid, s_mid)) / s_mid
+        x = x + d_mid * (s_down - s)
+        x = x + eps_fn(x) * s_up
+    return x.clamp(-1.0, 1.0)

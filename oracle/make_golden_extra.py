@@ -37,6 +37,15 @@ def main():
     save("dpm2m_small", noise=noise, sigmas=sig, out=out, nfe=np.int64(len(calls)), sigmas2=sig2, out2=out2,
          cfg=np.array([C, layers, cycle, B, L, seed, N], dtype=np.int64))
 
+    # ---- ancestral DPM-Solver-2 (the reference's default sampler); noise replayed from the recorded seed ----
+    N2 = 6
+    sig3 = ref.scheduler.KarrasSchedule(0.002, 80.0, 7.0, N2)()
+    torch.manual_seed(909)
+    out3 = ref.stochastic_sampler_edm.ADPM2Sampler(rho=1.0, num_steps=N2)(noise, fn=diff.denoise_fn, net=adapter, sigmas=sig3)
+    out3b = ref.stochastic_sampler_edm.ADPM2Sampler(rho=7.0, num_steps=N2, eta=0.0)(noise, fn=diff.denoise_fn, net=adapter, sigmas=sig3)
+    save("adpm2_small", noise=noise, sigmas=sig3, out=out3, out_rho7_eta0=out3b, seed=np.int64(909),
+         cfg=np.array([C, layers, cycle, B, L, seed, N2], dtype=np.int64))
+
     # ---- EMA classes on a tiny module ----
     phema = importlib.import_module("src.models.phema")
     torch.manual_seed(5)

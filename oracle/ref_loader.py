@@ -38,6 +38,7 @@ def import_reference():
     mods.sampler_edm = importlib.import_module("src.models.components.sampler_edm")
     mods.scheduler = importlib.import_module("src.models.components.scheduler")
     mods.distribution = importlib.import_module("src.models.components.distribution")
+    mods.stochastic_sampler_edm = importlib.import_module("src.models.components.stochastic_sampler_edm")
     return mods
 
 

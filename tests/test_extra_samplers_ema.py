@@ -90,3 +90,44 @@ def test_ema_classes_gpu_vs_reference_golden():
     m = tr.get()
     assert rel_l2(torch.cat([p.reshape(-1) for p in m.parameters()]), g["trad"]) < 1e-6
     assert [sfx for _, sfx in pf.get()] == ["-0.050", "-0.100"]
+
+
+def _adpm2_eps(g, B, L, steps):
+    torch.manual_seed(int(g["seed"]))
+    return torch.stack([torch.randn(B, 1, L) for _ in range(steps - 1)])       # one randn_like per step, in order
+
+
+def test_oracle_adpm2_matches_reference():
+    from oracle import edm, wavenet as owav
+    from oracle.weights import make_wavenet_state_dict
+    g = load_golden("adpm2_small")
+    C, layers, cycle, B, L, seed, steps = (int(v) for v in g["cfg"])
+    net_fn = owav.make_net_fn(make_wavenet_state_dict(C, layers, seed), cycle)
+    den = lambda x, s: edm.denoise(x, net_fn, 0.2, sigma=float(s))          # noqa: E731
+    it = iter(_adpm2_eps(g, B, L, steps))
+    with torch.no_grad():
+        out = edm.adpm2_sampler(torch.from_numpy(g["noise"]), den, torch.from_numpy(g["sigmas"]), steps, eps_fn=lambda x: next(it))
+        out0 = edm.adpm2_sampler(torch.from_numpy(g["noise"]), den, torch.from_numpy(g["sigmas"]), steps, rho=7.0, eta=0.0)
+    assert rel_l2(out, g["out"]) < 1e-5 and rel_l2(out0, g["out_rho7_eta0"]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_adpm2_sampler_gpu_vs_reference_golden():
+    from audiodiffuser_b200 import ADPM2Sampler, EluDiffusion, WaveNetNoise, _native as N
+    from oracle.weights import make_wavenet_state_dict
+    dev = torch.device("cuda:0")
+    g = load_golden("adpm2_small")
+    C, layers, cycle, B, L, seed, steps = (int(v) for v in g["cfg"])
+    net = WaveNetNoise(C, layers, cycle, precision="fp32")
+    net.load_state_dict(make_wavenet_state_dict(C, layers, seed), strict=True)
+    net = net.to(dev)
+    diff = EluDiffusion(0.2)
+    noise, sig = torch.from_numpy(g["noise"]).to(dev), torch.from_numpy(g["sigmas"]).to(dev)
+    smp = ADPM2Sampler(rho=1.0, num_steps=steps)
+    out = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig, eps=_adpm2_eps(g, B, L, steps).to(dev))
+    assert smp.last_nfe == 2 * (steps - 1)
+    out0 = ADPM2Sampler(rho=7.0, num_steps=steps, eta=0.0)(noise, fn=diff.denoise_fn, net=net, sigmas=sig)
+    N.check_async()
+    e, e0 = rel_l2(out, g["out"]), rel_l2(out0, g["out_rho7_eta0"])
+    print(f"ADPM2 fp32: rel-L2 {e:.3e} (ancestral noise replayed), {e0:.3e} (eta = 0, rho = 7)")
+    assert e < 2e-5 and e0 < 2e-5
