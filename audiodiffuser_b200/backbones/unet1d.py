@@ -185,6 +185,13 @@ class UNet1dBase(nn.Module):
     def _param_key(self):
         return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle carry the parameters only (EMA snapshots, diffunet_complex_module.py:162-167): packed
+        weights, workspaces and captured CUDA graphs are rebuilt lazily by the copy."""
+        state = self.__dict__.copy()
+        state.update(_packed=None, _packed_key=None, _graphs={})
+        return state
+
     def _pack(self):
         key = self._param_key()
         if self._packed is not None and key == self._packed_key:

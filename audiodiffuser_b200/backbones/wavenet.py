@@ -145,6 +145,15 @@ class WaveNetNoise(nn.Module):
         except Exception:
             pass
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle (the reference deep-copies and pickles the net for its EMA snapshots,
+        diffunet_complex_module.py:162-167, phema.py:96) carry the parameters only: the native handle and the
+        scratch buffers belong to THIS object and are rebuilt lazily by the copy."""
+        state = self.__dict__.copy()
+        state.update(_handle=None, _handle_key=None, _handle_dev=None, _ws={})
+        state.pop("_last_flat_grad", None)
+        return state
+
     def _workspace(self, B, L, prec, device):
         """(aligned pointer, byte count) of a cached scratch buffer large enough for (B, L, precision)."""
         need = N.lib().adb_wavenet_workspace_bytes(self._native(), B, L, prec)

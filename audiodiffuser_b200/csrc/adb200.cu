@@ -211,6 +211,18 @@ extern "C" int adb_ema_lerp(float* ema, const float* params, float weight, int64
     return ADB_OK;
 }
 
+extern "C" int adb_pcm16_encode(const float* x, int16_t* pcm, int64_t n, void* stream) {
+    REQUIRE(x && pcm && n > 0, "adb_pcm16_encode: bad arguments");
+    const bool vec = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(pcm) % 16 == 0);
+    const int64_t items = vec ? (n + 7) / 8 : n;
+    const int64_t blocks = std::min<int64_t>((items + 255) / 256, 148 * 16);
+    KL(1);
+    if (vec) pcm16_kernel<true><<<(unsigned)blocks, 256, 0, S(stream)>>>(x, pcm, n);
+    else     pcm16_kernel<false><<<(unsigned)blocks, 256, 0, S(stream)>>>(x, pcm, n);
+    CK(cudaGetLastError());
+    return ADB_OK;
+}
+
 extern "C" int adb_edm_heun_mid(const float* x, const float* f1, float sigma, float sigma_data, float h, float* d, float* x1,
                                 int64_t n, void* stream) {
     REQUIRE(x && f1 && d && x1 && n > 0, "adb_edm_heun_mid: bad arguments");

@@ -255,4 +255,30 @@ inline cudaError_t edm_launch(const EdmArgs& p, const float* in3, cudaStream_t s
     return cudaGetLastError();
 }
 
+// float -> 16-bit PCM (round half to even of x * 2^15, saturated): the device half of writing 16-bit WAV files.
+__device__ __forceinline__ short pcm16_of(float v) {
+    const int q = __float2int_rn(v * 32768.0f);          // NaN -> 0, +-inf saturate to int32
+    return (short)max(-32768, min(32767, q));
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) pcm16_kernel(const float* __restrict__ x, short* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        const long long nv = n / 8;
+        for (; i < nv; i += stride) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+            union { short s[8]; uint4 u; } r;
+            r.s[0] = pcm16_of(a.x); r.s[1] = pcm16_of(a.y); r.s[2] = pcm16_of(a.z); r.s[3] = pcm16_of(a.w);
+            r.s[4] = pcm16_of(b.x); r.s[5] = pcm16_of(b.y); r.s[6] = pcm16_of(b.z); r.s[7] = pcm16_of(b.w);
+            reinterpret_cast<uint4*>(out)[i] = r.u;
+        }
+        if (i == nv) for (long long j = nv * 8; j < n; ++j) out[j] = pcm16_of(x[j]);   // ragged tail: one thread
+    } else {
+        for (; i < n; i += stride) out[i] = pcm16_of(x[i]);
+    }
+}
+
 }  // namespace adb

@@ -20,16 +20,22 @@ def shard_range(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def shard_noise(global_batch: int, rank: int, world: int, length: int, base_seed: int = 0, channels: int = 1) -> torch.Tensor:
-    """N(0,1) noise [B_local, channels, length] (CPU, fp32) for this rank's shard; row i is drawn from
-    torch.Generator().manual_seed(base_seed + global_index)."""
-    start, stop = shard_range(global_batch, rank, world)
-    out = torch.empty(stop - start, channels, length, dtype=torch.float32)
+def noise_for_indices(indices, length: int, base_seed: int = 0, channels: int = 1) -> torch.Tensor:
+    """N(0,1) noise [len(indices), channels, length] (CPU, fp32, pinned when CUDA is present); the row of global sample
+    `g` is drawn from torch.Generator().manual_seed(base_seed + g), whatever rank or batch it lands in."""
+    indices = list(indices)
+    out = torch.empty(len(indices), channels, length, dtype=torch.float32, pin_memory=torch.cuda.is_available())
     g = torch.Generator()
-    for i, gi in enumerate(range(start, stop)):
+    for i, gi in enumerate(indices):
         g.manual_seed(base_seed + gi)
         out[i] = torch.randn(channels, length, generator=g)
     return out
+
+
+def shard_noise(global_batch: int, rank: int, world: int, length: int, base_seed: int = 0, channels: int = 1) -> torch.Tensor:
+    """Noise for this rank's contiguous shard of the global batch (see noise_for_indices)."""
+    start, stop = shard_range(global_batch, rank, world)
+    return noise_for_indices(range(start, stop), length, base_seed, channels)
 
 
 def gather_shards(local: torch.Tensor, global_batch: int, rank: int, world: int):

@@ -81,6 +81,10 @@ int adb_edm_clamp(const float* x_dev, float* out_dev, int64_t n, void* stream);
 /* ema = torch.lerp(ema, params, weight) on flat vectors, in place — PowerFunctionEMA.update / TraditionalEMA.update
  * (src/models/phema.py:104-108, :145-151), one launch per EMA instead of one per parameter tensor */
 int adb_ema_lerp(float* ema_dev, const float* params_dev, float weight, int64_t n, void* stream);
+/* pcm[i] = saturate_int16(round_half_even(x[i] * 32768)) — the float -> 16-bit PCM conversion behind
+ * torchaudio.save(..., bits_per_sample=16) of the generated test samples (src/models/diffunet_complex_module.py:263-266),
+ * done on the device so only 2 bytes per sample cross PCIe. NaN -> 0. 6 bytes of HBM traffic per sample. */
+int adb_pcm16_encode(const float* x_dev, int16_t* pcm_dev, int64_t n, void* stream);
 
 /* Fused Heun step around RAW network outputs F (what the fused trajectory launches between network
  * evaluations; sampler_edm.py:350-367 with diffusion.py:60-63 inlined):
