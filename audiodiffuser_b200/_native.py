@@ -38,6 +38,7 @@ _SIGS = {
     "adb_edm_lincomb": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_int64, c_void_p]),
     "adb_edm_clamp": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "adb_ema_lerp": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p]),
+    "adb_edm_lincomb_n": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "adb_pcm16_encode": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "adb_edm_heun_mid": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "adb_edm_heun_post": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_int64, c_void_p]),

@@ -322,3 +322,7 @@ class ADPM2Sampler(nn.Module):
         out = torch.empty_like(x)
         N.check(lib.adb_edm_clamp(N.ptr(x), N.ptr(out), n, st))
         return out
+
+
+# The reference keeps these two in the same module (sampler_edm.py:495, :807); re-exported so `_target_` paths carry over.
+from .sampler_dpm import DPMSampler, UniPCSampler  # noqa: E402,F401

@@ -211,6 +211,28 @@ extern "C" int adb_ema_lerp(float* ema, const float* params, float weight, int64
     return ADB_OK;
 }
 
+extern "C" int adb_edm_lincomb_n(const float* x, float a, const float* const* terms, const float* coefs, int k, int clamp,
+                                 float* out, int64_t n, void* stream) {
+    REQUIRE(x && out && n > 0, "adb_edm_lincomb_n: bad arguments");
+    REQUIRE(k >= 0 && k <= 4, "adb_edm_lincomb_n: 0..4 terms supported, got %d", k);
+    REQUIRE(k == 0 || (terms && coefs), "adb_edm_lincomb_n: terms / coefs missing");
+    LincombArgs p{};
+    p.x = x; p.a = a; p.out = out; p.n = n; p.clamp = clamp;
+    for (int i = 0; i < k; ++i) {
+        REQUIRE(terms[i], "adb_edm_lincomb_n: term %d is NULL", i);
+        p.m[i] = terms[i]; p.c[i] = coefs[i];
+    }
+    KL(1);
+    switch (k) {
+        case 0: CK(lincomb_n_launch<0>(p, S(stream))); break;
+        case 1: CK(lincomb_n_launch<1>(p, S(stream))); break;
+        case 2: CK(lincomb_n_launch<2>(p, S(stream))); break;
+        case 3: CK(lincomb_n_launch<3>(p, S(stream))); break;
+        default: CK(lincomb_n_launch<4>(p, S(stream))); break;
+    }
+    return ADB_OK;
+}
+
 extern "C" int adb_pcm16_encode(const float* x, int16_t* pcm, int64_t n, void* stream) {
     REQUIRE(x && pcm && n > 0, "adb_pcm16_encode: bad arguments");
     const bool vec = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(pcm) % 16 == 0);

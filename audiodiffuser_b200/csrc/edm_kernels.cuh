@@ -255,6 +255,64 @@ inline cudaError_t edm_launch(const EdmArgs& p, const float* in3, cudaStream_t s
     return cudaGetLastError();
 }
 
+// out = a x + sum_{k<K} c[k] m[k]  (optionally clamped to [-1, 1]): the update of every DPM-Solver / UniPC step is such a
+// combination of the state and up to four network outputs with host-computed scalars (sampler_edm.py:562-704, :870-987).
+// (K + 2) * 4 bytes of HBM traffic per element, one launch per update.
+struct LincombArgs {
+    const float* x;
+    const float* m[4];
+    float a, c[4];
+    float* out;
+    long long n;
+    int clamp;
+};
+
+template <int K, bool VEC>
+__global__ void __launch_bounds__(256) lincomb_n_kernel(LincombArgs p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        const long long nv = p.n / 4;
+        for (; i < nv; i += stride) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x) + i);
+            float4 mv[K > 0 ? K : 1];
+#pragma unroll
+            for (int k = 0; k < K; ++k) mv[k] = __ldg(reinterpret_cast<const float4*>(p.m[k]) + i);
+            float4 r = make_float4(p.a * xv.x, p.a * xv.y, p.a * xv.z, p.a * xv.w);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                r.x = fmaf(p.c[k], mv[k].x, r.x); r.y = fmaf(p.c[k], mv[k].y, r.y);
+                r.z = fmaf(p.c[k], mv[k].z, r.z); r.w = fmaf(p.c[k], mv[k].w, r.w);
+            }
+            if (p.clamp) {
+                r.x = fminf(fmaxf(r.x, -1.f), 1.f); r.y = fminf(fmaxf(r.y, -1.f), 1.f);
+                r.z = fminf(fmaxf(r.z, -1.f), 1.f); r.w = fminf(fmaxf(r.w, -1.f), 1.f);
+            }
+            reinterpret_cast<float4*>(p.out)[i] = r;
+        }
+    } else {
+        for (; i < p.n; i += stride) {
+            float r = p.a * p.x[i];
+#pragma unroll
+            for (int k = 0; k < K; ++k) r = fmaf(p.c[k], p.m[k][i], r);
+            if (p.clamp) r = fminf(fmaxf(r, -1.f), 1.f);
+            p.out[i] = r;
+        }
+    }
+}
+
+template <int K>
+inline cudaError_t lincomb_n_launch(const LincombArgs& p, cudaStream_t stream) {
+    auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool vec = (p.n % 4 == 0) && aligned(p.x) && aligned(p.out);
+    for (int k = 0; k < K; ++k) vec = vec && aligned(p.m[k]);
+    const long long work = vec ? p.n / 4 : p.n;
+    const long long blocks = std::min<long long>((work + 255) / 256, 148LL * 16);
+    if (vec) lincomb_n_kernel<K, true><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else     lincomb_n_kernel<K, false><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 // float -> 16-bit PCM (round half to even of x * 2^15, saturated): the device half of writing 16-bit WAV files.
 __device__ __forceinline__ short pcm16_of(float v) {
     const int q = __float2int_rn(v * 32768.0f);          // NaN -> 0, +-inf saturate to int32

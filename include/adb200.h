@@ -76,6 +76,12 @@ int adb_edm_rk2(const float* x_dev, const float* d_dev, const float* x1_dev, con
  * out = a x - e (c0 d - c1 d_old)       (second-order multistep, sampler_edm.py:1100-1108) */
 int adb_edm_lincomb(const float* x_dev, const float* d_dev, const float* d_old_dev, float a, float e, float c0, float c1,
                     float* out_dev, int64_t n, void* stream);
+/* out = a x + sum_{i<k} coefs[i] terms[i]   (k <= 4; clamped to [-1, 1] when `clamp` != 0). `terms` is a HOST array of k
+ * device pointers, `coefs` a host array of k scalars. One launch per update of the reference's DPMSampler (single-step
+ * DPM-Solver-1/2/3 and multistep order 1-3, sampler_edm.py:562-704) and UniPCSampler (:870-987): every such update is a
+ * combination of the state and the stored network outputs with scalars that depend only on the time grid. */
+int adb_edm_lincomb_n(const float* x_dev, float a, const float* const* terms, const float* coefs, int k, int clamp,
+                      float* out_dev, int64_t n, void* stream);
 /* out = clamp(x, -1, 1)                 (the final x.clamp of DPM2MSampler.forward, sampler_edm.py:1131) */
 int adb_edm_clamp(const float* x_dev, float* out_dev, int64_t n, void* stream);
 /* ema = torch.lerp(ema, params, weight) on flat vectors, in place — PowerFunctionEMA.update / TraditionalEMA.update
