@@ -346,7 +346,8 @@ struct adb_wavenet {
     float* wspT = nullptr;            // [co][ci] (training step)
     float* d_scale = nullptr;         // g / ||v|| per weight-normed conv: [0] input, [1 + 2l] dilated, [2 + 2l] output, [last] skip
     WnJob* d_jobs = nullptr;
-    float* wpT = nullptr;             // [512][C] scratch of refold
+    float* wpT = nullptr;             // [layers][512][C] transposed diffusion projections (refold)
+    const float** fold_tab = nullptr; // 6 x (layers*3) operand pointers of the two batched fold GEMMs (refold)
     float* w1perm = nullptr;          // [3][C][2C] scratch of refold (column-permuted W1)
     std::vector<int64_t> counts, dst_off;   // flat-vector pieces (state_dict order) and their offsets in `params`
     const float** d_wp = nullptr;     // device arrays of per-layer pointers
@@ -526,20 +527,23 @@ static int refold(adb_wavenet* n) {
             cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(n->w1perm, w.w1p, C, 2 * C, 3);
             cl_pack_conv_tc_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2T, w.w2Tp, 2 * C, C, 1);
             cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1d, w.w1dp, 2 * C, C, 3);
-            transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, n->wpT, C, 512);     // [C][512] -> [512][C] (stream-ordered reuse)
-            for (int tap = 0; tap < 3; ++tap) {
-                ConvF32Args a;
-                memset(&a, 0, sizeof a);
-                // mtab[k][l,tap,co] = sum_ci Wp[ci][k] * W1[tap][ci][co]
-                a.in = n->wpT; a.w = w.w1f + static_cast<size_t>(tap) * C * 2 * C; a.out = n->mtab + (l * 3 + tap) * 512;
-                a.nb = 1; a.L = 512; a.Cin = C; a.Cout = 2 * C; a.taps = 1; a.dil = 1;
-                a.ldw = 2 * C; a.ldo = ldm; a.in_scale = 1.f;
-                CK(conv_cl_f32(a, 0));
-                // cvec[l,tap,co] = sum_ci bp[ci] * W1[tap][ci][co] (+ b1[co] for the centre tap)
-                a.in = w.bp; a.out = n->cvec + (l * 3 + tap) * 512; a.L = 1; a.ldo = 2 * C;
-                a.bias = (tap == 1) ? w.b1 : nullptr;
-                CK(conv_cl_f32(a, 0));
-            }
+            transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, n->wpT + static_cast<size_t>(l) * 512 * C, C, 512);   // [C][512] -> [512][C]
+        }
+        {
+            // Step-embedding fold tables for all layers and taps in two launches (operands through pointer tables):
+            //   mtab[k][l,tap,co] = sum_ci Wp_l[ci][k] * W1_l[tap][ci][co]
+            //   cvec[l,tap,co]    = sum_ci bp_l[ci]    * W1_l[tap][ci][co] (+ b1_l[co] for the centre tap)
+            const int nb = layers * 3;
+            ConvF32Args a;
+            memset(&a, 0, sizeof a);
+            a.nb = nb; a.Cin = C; a.Cout = 2 * C; a.taps = 1; a.dil = 1; a.ldw = 2 * C; a.in_scale = 1.f;
+            a.w_tab = n->fold_tab + 1 * nb;
+            a.in_tab = n->fold_tab + 0 * nb; a.out_tab = const_cast<float* const*>(n->fold_tab + 2 * nb); a.bias_tab = nullptr;
+            a.L = 512; a.ldo = ldm;
+            CK(conv_cl_f32(a, 0));
+            a.in_tab = n->fold_tab + 3 * nb; a.out_tab = const_cast<float* const*>(n->fold_tab + 4 * nb); a.bias_tab = n->fold_tab + 5 * nb;
+            a.L = 1; a.ldo = 2 * C;
+            CK(conv_cl_f32(a, 0));
         }
         pack_tc_tail_kernel<<<64, 256>>>(n->wsp_f, n->wsp_tc);
         CK(cudaGetLastError());
@@ -631,7 +635,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     CKN(dmalloc(n, &n->w_in_f, C));
     CKN(dmalloc(n, &n->wsp_f, static_cast<size_t>(C) * C));
     CKN(dmalloc(n, &n->wspT, static_cast<size_t>(C) * C));
-    CKN(dmalloc(n, &n->wpT, 512ULL * C));
+    CKN(dmalloc(n, &n->wpT, static_cast<size_t>(layers) * 512 * C));
     CKN(dmalloc(n, &n->w1perm, 3ULL * C * 2 * C));
     std::vector<const float*> h_wp(layers), h_bp(layers);
     for (int l = 0; l < layers; ++l) {
@@ -660,6 +664,22 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         const long long ldm = static_cast<long long>(layers) * 1536;
         CKN(dmalloc(n, &n->mtab, 512ULL * ldm));
         CKN(dmalloc(n, &n->cvec, static_cast<size_t>(ldm)));
+        {
+            const int nb = layers * 3;
+            std::vector<const float*> tab(6 * static_cast<size_t>(nb), nullptr);
+            for (int l = 0; l < layers; ++l)
+                for (int tap = 0; tap < 3; ++tap) {
+                    const int e = l * 3 + tap;
+                    tab[0 * nb + e] = n->wpT + static_cast<size_t>(l) * 512 * C;                       // mtab: input
+                    tab[1 * nb + e] = n->L[l].w1f + static_cast<size_t>(tap) * C * 2 * C;              // both: weights
+                    tab[2 * nb + e] = n->mtab + static_cast<size_t>(e) * 512;                          // mtab: output
+                    tab[3 * nb + e] = n->L[l].bp;                                                      // cvec: input
+                    tab[4 * nb + e] = n->cvec + static_cast<size_t>(e) * 512;                          // cvec: output
+                    tab[5 * nb + e] = (tap == 1) ? n->L[l].b1 : nullptr;                               // cvec: bias
+                }
+            CKN(dmalloc(n, &n->fold_tab, tab.size()));
+            CKN(cudaMemcpy(n->fold_tab, tab.data(), sizeof(float*) * tab.size(), cudaMemcpyHostToDevice));
+        }
         int rc2 = make_weight_map(&n->tm_w, n->wtc, static_cast<uint64_t>(layers) * 32 * 256);
         if (!rc2) rc2 = make_weight_map(&n->tm_w2, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 128);
         if (!rc2) rc2 = make_weight_map(&n->tm_w4, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 64);

@@ -90,6 +90,13 @@ struct ConvF32Args {
     long long ldo;       // row pitch of out (>= Cout)
     float in_scale;
     int relu;
+    // optional per-batch-entry operand tables (device arrays of nb pointers): entry b then uses in_tab[b] / w_tab[b] /
+    // bias_tab[b] (may hold NULL) / out_tab[b] instead of the strided operands above — one launch for many small GEMMs
+    // with unrelated operands (the per-layer, per-tap step-embedding fold tables).
+    const float* const* in_tab;
+    const float* const* w_tab;
+    const float* const* bias_tab;
+    float* const* out_tab;
 };
 
 __global__ void __launch_bounds__(256) conv_cl_f32_kernel(ConvF32Args p) {
@@ -102,7 +109,9 @@ __global__ void __launch_bounds__(256) conv_cl_f32_kernel(ConvF32Args p) {
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;      // thread tile: rows ty*4.., cols tx*4..
     float acc[4][4] = {};
-    const float* inb = p.in + static_cast<long long>(b) * p.L * p.Cin;
+    const float* inb = p.in_tab ? p.in_tab[b] : p.in + static_cast<long long>(b) * p.L * p.Cin;
+    const float* wb = p.in_tab ? p.w_tab[b] : p.w;
+    const float* biasb = p.in_tab ? (p.bias_tab ? p.bias_tab[b] : nullptr) : p.bias;
     const float* paddb = p.padd ? p.padd + static_cast<long long>(b) * p.Cin : nullptr;
     const int ksteps = p.taps * p.Cin / BK;
     // A-load mapping: 64 rows x 16 k = 1024 floats, 4 per thread: row = tid/4, k4 = (tid%4)*4
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(256) conv_cl_f32_kernel(ConvF32Args p) {
             As[a_k + 0][a_row] = v.x; As[a_k + 1][a_row] = v.y; As[a_k + 2][a_row] = v.z; As[a_k + 3][a_row] = v.w;
         }
         {
-            const float4 v = *reinterpret_cast<const float4*>(p.w + static_cast<long long>(kglob + b_k) * p.ldw + n0 + b_c);
+            const float4 v = *reinterpret_cast<const float4*>(wb + static_cast<long long>(kglob + b_k) * p.ldw + n0 + b_c);
             *reinterpret_cast<float4*>(&Bs[b_k][b_c]) = v;
         }
         __syncthreads();
@@ -153,11 +162,11 @@ __global__ void __launch_bounds__(256) conv_cl_f32_kernel(ConvF32Args p) {
         __syncthreads();
     }
     float bias[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.bias) {
-        const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + tx * 4);
+    if (biasb) {
+        const float4 bb = *reinterpret_cast<const float4*>(biasb + n0 + tx * 4);
         bias[0] = bb.x; bias[1] = bb.y; bias[2] = bb.z; bias[3] = bb.w;
     }
-    float* outb = p.out + static_cast<long long>(b) * p.L * p.ldo;
+    float* outb = p.in_tab ? p.out_tab[b] : p.out + static_cast<long long>(b) * p.L * p.ldo;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int t = t0 + ty * 4 + i;

@@ -193,7 +193,7 @@ def run_unet(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or 32
+    B = args.batch or 128
     torch.manual_seed(0)
     net = UNet1dBase(precision=args.precision, **UNET_CFG4)
     net.unet.to_out.to_out.weight.data.uniform_(-0.06, 0.06)          # zero-initialised in the reference (unet1d.py:619)
@@ -269,7 +269,7 @@ def run_unet(args, rank, world, local_rank):
         line["roofline"] = {"bound": "tensor", "kernel": "whole network evaluation (cl_conv_tc_kernel is 46 % of it, profiles/r1_launches_unet1d_b32.csv)",
                             "achieved": line["effective_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": line["effective_tflops"] / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"]}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # host baseline: rank 0 at N = 1 only
             from oracle import unet1d as ounet
             from oracle.weights import make_unet1d_state_dict
             threads = os.cpu_count() or 1
@@ -377,7 +377,7 @@ def run_train(args, rank, world, local_rank):
                                                           "3 x 606 GFLOP per sample)",
                             "achieved": line["effective_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": line["effective_tflops"] / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"]}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # host baseline: rank 0 at N = 1 only
             from oracle import edm as oedm, wavenet as owav
             from oracle.weights import make_wavenet_state_dict
             threads = os.cpu_count() or 1
@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 32 UNet1d / 16 train)")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 128 UNet1d / 16 train)")
     ap.add_argument("--workload", default="diffwave", choices=["diffwave", "unet1d", "train"],
                     help="diffwave = the headline metric (BASELINE.json configs[1]); unet1d = configs[3]")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -535,7 +535,7 @@ def main():
                 "roofline": roofline, "roofline_step_kernel": step_roofline,
                 "kernel_ms": {k: v[0] for k, v in tm.items()},
                 "clocks": clk}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # host baseline: rank 0 at N = 1 only
             threads = os.cpu_count() or 1
             t = cpu_reference_eval_time(4, threads)
             t_eval = sum(t[1:]) / len(t[1:])
