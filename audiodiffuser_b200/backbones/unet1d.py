@@ -303,6 +303,14 @@ class UNet1dBase(nn.Module):
             pk = torch.empty(lib.adb_cl_wavdec_packed_elems(nf), dtype=torch.bfloat16, device=dev)
             N.check(lib.adb_cl_wavdec_pack(N.ptr(P["to_out.to_out.weight"]), N.ptr(pk), nf, cout_w, W, S, st))
             P["to_out.packed"] = pk
+        cin_w = cfg["in_channels"]
+        if bf16 and W == 2 * S and (W * cin_w) % 64 == 0 and (2 * nf) % 64 == 0:   # WAVenc on the tensor cores (see adb_cl_wavenc_prep)
+            wk = sd["to_in.to_in.weight"].permute(2, 1, 0).reshape(W * cin_w, nf)   # row k*Cin + c, column f
+            wc = torch.zeros(2, W * cin_w, 2 * nf, device=dev)
+            wc[0, :, :nf] = wk                                    # even frame 2m: buffer row m
+            wc[0, S * cin_w:, nf:] = wk[:S * cin_w]               # odd frame 2m+1: second half of row m ...
+            wc[1, :S * cin_w, nf:] = wk[S * cin_w:]               # ... and first half of row m+1
+            P["to_in.tc"] = gemm_weight(wc, None, dict(off0=0, dil=1, ups=0))
         P["cond_w"] = torch.cat(cond_w, dim=0).contiguous()
         P["cond_b"] = torch.cat(cond_b, dim=0).contiguous()
         P["cond_off"] = cond_off
@@ -411,8 +419,17 @@ class UNet1dBase(nn.Module):
         nf = cfg["num_filters"]
         pad = W // 2 - S // 2
         Lc = (L + 2 * pad - W) // S + 1
-        h = torch.empty(B, Lc, nf, dtype=adt, device=dev)
-        N.check(lib.adb_cl_wavenc(N.ptr(x), N.ptr(P["to_in.to_in.weight"]), N.ptr(h), B, cin, L, nf, W, S, dt, st))
+        if "to_in.tc" in P and L % W == 0:
+            ent, rows = P["to_in.tc"], L // W
+            xb = torch.empty(B, rows + 1, W * cin, dtype=adt, device=dev)
+            N.check(lib.adb_cl_wavenc_prep(N.ptr(x), N.ptr(xb), B, cin, L, W, S, st))
+            h = torch.empty(B, rows, 2 * nf, dtype=adt, device=dev)
+            N.check(lib.adb_cl_conv(N.ptr(xb), N.ptr(ent["w"]), N.ptr(None), N.ptr(None), N.ptr(h), B, rows + 1, rows, W * cin, 2 * nf,
+                                    2, 0, 1, ACT_NONE, 0, 0, 0, dt, st))
+            h = h.view(B, Lc, nf)                                # row m holds frames 2m and 2m+1
+        else:
+            h = torch.empty(B, Lc, nf, dtype=adt, device=dev)
+            N.check(lib.adb_cl_wavenc(N.ptr(x), N.ptr(P["to_in.to_in.weight"]), N.ptr(h), B, cin, L, nf, W, S, dt, st))
 
         n = len(cfg["multipliers"]) - 1
         skip_scale = 2 ** -0.5 if cfg["use_skip_scale"] else 1.0

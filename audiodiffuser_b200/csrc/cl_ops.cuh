@@ -297,47 +297,89 @@ __global__ void __launch_bounds__(256) cl_layernorm_kernel(const T* __restrict__
 // fp32. q: [B][L][C], kv: [B][L][2C] (k = first C columns, v = last C), out: [B][L][C]; head h owns columns
 // [h*d, (h+1)*d). K and V of one (b, h) live in shared memory; one warp per query row.
 // ------------------------------------------------------------------------------------------------
+constexpr int CL_ATT_KPAD = 4;      // K rows padded to d + 4 floats: 16-byte aligned rows whose float4 loads are bank-conflict free
 template <typename T>
 __global__ void __launch_bounds__(256) cl_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out,
                                                            int L, int C, int heads) {
-    extern __shared__ float smem_att[];
-    const int d = C / heads;
+    extern __shared__ __align__(16) float smem_att[];
+    const int d = C / heads;                    // d % 4 == 0 (checked by the caller)
+    const int ldk = d + CL_ATT_KPAD;
+    const int Lp = (L + 3) & ~3;
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-    float* Ks = smem_att;                       // [L][d + 1]
-    float* Vs = Ks + static_cast<size_t>(L) * (d + 1);   // [L][d]
-    float* Ps = Vs + static_cast<size_t>(L) * d;         // [warps][L]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float* Ks = smem_att;                                  // [L][d + 4]
+    float* Vs = Ks + static_cast<size_t>(L) * ldk;         // [L][d]
+    float* Ps = Vs + static_cast<size_t>(L) * d;           // [warps][Lp]
+    float* Qs = Ps + static_cast<size_t>(nwarps) * Lp;     // [warps][d]
     const T* kvb = kv + static_cast<long long>(b) * L * 2 * C;
     for (int i = threadIdx.x; i < L * d; i += blockDim.x) {
         const int r = i / d, c = i % d;
-        Ks[r * (d + 1) + c] = cl_ld<T>(kvb + static_cast<long long>(r) * 2 * C + h * d + c);
+        Ks[r * ldk + c] = cl_ld<T>(kvb + static_cast<long long>(r) * 2 * C + h * d + c);
         Vs[r * d + c] = cl_ld<T>(kvb + static_cast<long long>(r) * 2 * C + C + h * d + c);
     }
     __syncthreads();
     const float scale = rsqrtf(static_cast<float>(d));
-    float* P = Ps + static_cast<size_t>(warp) * L;
+    float* P = Ps + static_cast<size_t>(warp) * Lp;
+    float* Q = Qs + static_cast<size_t>(warp) * d;
     for (int qi = blockIdx.y * nwarps + warp; qi < L; qi += gridDim.y * nwarps) {
         const T* qr = q + (static_cast<long long>(b) * L + qi) * C + h * d;
+        for (int c = lane; c < d; c += 32) Q[c] = cl_ld<T>(qr + c);        // the query row once, then shared-memory broadcasts
+        __syncwarp();
         float mx = -INFINITY;
-        for (int j = lane; j < L; j += 32) {
-            float s = 0.f;
-            for (int c = 0; c < d; ++c) s = fmaf(cl_ld<T>(qr + c), Ks[j * (d + 1) + c], s);
-            s *= scale;
-            P[j] = s;
-            mx = fmaxf(mx, s);
+        for (int j0 = 0; j0 < L; j0 += 128) {                              // four keys per lane share every q broadcast
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+            const float4* kr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                kr[u] = reinterpret_cast<const float4*>(Ks + static_cast<size_t>(min(j0 + lane + 32 * u, L - 1)) * ldk);
+            const float4* q4 = reinterpret_cast<const float4*>(Q);
+            for (int c = 0; c < d / 4; ++c) {                              // same summation order as a scalar loop over c
+                const float4 qv = q4[c];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 kk = kr[u][c];
+                    s[u] = fmaf(qv.x, kk.x, s[u]); s[u] = fmaf(qv.y, kk.y, s[u]);
+                    s[u] = fmaf(qv.z, kk.z, s[u]); s[u] = fmaf(qv.w, kk.w, s[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + lane + 32 * u;
+                if (j < L) { P[j] = s[u] * scale; mx = fmaxf(mx, s[u] * scale); }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float sum = 0.f;
-        for (int j = lane; j < L; j += 32) { const float e = expf(P[j] - mx); P[j] = e; sum += e; }
+        for (int j = lane; j < Lp; j += 32) {
+            const float e = j < L ? expf(P[j] - mx) : 0.f;                 // the pad of P is zero so the loop below can run by fours
+            P[j] = e;
+            sum += e;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         __syncwarp();
         const float inv = 1.0f / sum;
-        for (int c = lane; c < d; c += 32) {
-            float acc = 0.f;
-            for (int j = 0; j < L; ++j) acc = fmaf(P[j] * inv, Vs[j * d + c], acc);
-            cl_st<T>(out + (static_cast<long long>(b) * L + qi) * C + h * d + c, acc);
+        for (int c0 = 0; c0 < d; c0 += 64) {                               // two adjacent value columns per lane, four keys per P load
+            const int ca = min(c0 + 2 * lane, d - 2);
+            const float* va = Vs + ca;
+            const float4* p4 = reinterpret_cast<const float4*>(P);
+            float a0 = 0.f, a1 = 0.f;
+            for (int j = 0; j < Lp; j += 4) {
+                const float4 p = p4[j >> 2];
+                const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 v = *reinterpret_cast<const float2*>(va + static_cast<size_t>(min(j + u, L - 1)) * d);
+                    a0 = fmaf(pv[u], v.x, a0);
+                    a1 = fmaf(pv[u], v.y, a1);
+                }
+            }
+            if (c0 + 2 * lane < d) {
+                T* orow = out + (static_cast<long long>(b) * L + qi) * C + h * d + ca;
+                cl_st<T>(orow, a0 * inv);
+                cl_st<T>(orow + 1, a1 * inv);
+            }
         }
         __syncwarp();
     }
@@ -659,8 +701,11 @@ __global__ void __launch_bounds__(256) cl_concat_vec_kernel(const T* __restrict_
 }
 
 // Batched small dense layer with the weights read ONCE for the whole batch: out[b][n] = act(bias[n] + sum_k W[n][k] f(in[b][k])).
-// The (optionally SiLU'd) inputs of up to 32 samples sit transposed in shared memory; lane = sample, one warp per output
-// column, weight rows loaded coalesced and broadcast with shuffles. grid (ceil(N / 8), ceil(B / 32)), smem = K * 32 floats.
+// The (optionally SiLU'd) inputs of up to 32 samples sit transposed in shared memory; lane = sample, one warp per group of
+// CL_LIN_COLS output columns (4 at a time share every staged input value), weight rows loaded coalesced and broadcast
+// with shuffles. grid (ceil(N / (8 * CL_LIN_COLS)), ceil(B / 32)), smem = K * 32 floats; the staging (and its expf) is
+// amortised over 8 * CL_LIN_COLS columns per CTA.
+constexpr int CL_LIN_COLS = 8;
 __global__ void __launch_bounds__(256) cl_linear_batched_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* __restrict__ out, int B, int K,
                                                                 int N, int silu_in, int act) {
@@ -668,26 +713,64 @@ __global__ void __launch_bounds__(256) cl_linear_batched_kernel(const float* __r
     const int b0 = blockIdx.y * 32;
     const int nb = min(32, B - b0);
     for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
-        const int k = i >> 5, bb = i & 31;
+        const int bb = i / K, k = i - bb * K;       // consecutive threads read consecutive k of one sample (coalesced)
         float v = 0.f;
         if (bb < nb) {
             v = in[static_cast<long long>(b0 + bb) * K + k];
             if (silu_in) v = v / (1.0f + expf(-v));
         }
-        xs[i] = v;
+        xs[k * 32 + bb] = v;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 8 + warp;
-    if (n >= N) return;
-    const float* wr = w + static_cast<long long>(n) * K;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 32) {
-        const float wv = (k0 + lane < K) ? wr[k0 + lane] : 0.f;
-        const int kn = min(32, K - k0);
-        for (int j = 0; j < kn; ++j) acc = fmaf(__shfl_sync(0xffffffffu, wv, j), xs[(k0 + j) * 32 + lane], acc);
+    const int nbase = (blockIdx.x * 8 + warp) * CL_LIN_COLS;
+    for (int g = 0; g < CL_LIN_COLS; g += 4) {
+        const int n = nbase + g;
+        if (n >= N) return;
+        const float* wr[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wr[c] = w + static_cast<long long>(min(n + c, N - 1)) * K;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            float wv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wv[c] = (k0 + lane < K) ? wr[c][k0 + lane] : 0.f;
+            const int kn = min(32, K - k0);
+            for (int j = 0; j < kn; ++j) {
+                const float xv = xs[(k0 + j) * 32 + lane];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] = fmaf(__shfl_sync(0xffffffffu, wv[c], j), xv, acc[c]);
+            }
+        }
+        if (lane < nb) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (n + c < N) out[static_cast<long long>(b0 + lane) * N + n + c] = cl_act(acc[c] + (bias ? bias[n + c] : 0.f), act);
+        }
     }
-    if (lane < nb) out[static_cast<long long>(b0 + lane) * N + n] = cl_act(acc + (bias ? bias[n] : 0.f), act);
+}
+
+// WAVenc1d on the tensor cores, step 1: x [B][Cin][L] channels-first fp32 -> bf16 channels-last rows [B][L/W + 1][W*Cin],
+// shifted right by `pad` samples (zeros in front and behind) so that buffer row m = samples [mW - pad, (m+1)W - pad): with
+// W = 2S an even output frame 2m reads exactly row m and an odd frame the second half of row m plus the first half of
+// row m+1 — a 2-tap GEMM-convolution over these rows (weights laid out by the host, audiodiffuser_b200/backbones/unet1d.py).
+__global__ void __launch_bounds__(256) cl_wavenc_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Cin,
+                                                             int L, long long Lp, int pad) {
+    const long long total = static_cast<long long>(B) * Lp;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / Lp, j = i - b * Lp;
+        const long long s = j - pad;
+        const bool in = s >= 0 && s < L;
+        const float* xb = x + b * Cin * static_cast<long long>(L) + s;
+        __nv_bfloat16* o = out + i * Cin;
+        if (Cin == 2) {
+            const float v0 = in ? __ldg(xb) : 0.f, v1 = in ? __ldg(xb + L) : 0.f;
+            *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v0, v1);
+        } else {
+            for (int c = 0; c < Cin; ++c) o[c] = __float2bfloat16(in ? __ldg(xb + static_cast<long long>(c) * L) : 0.f);
+        }
+    }
 }
 
 // WAVenc1d, register-tiled: thread = 4 consecutive output rows x 4 consecutive filters; per (channel, tap) one 16-byte

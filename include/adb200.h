@@ -227,6 +227,11 @@ int adb_cl_attention(const void* q_dev, const void* kv_dev, void* out_dev, int B
 /* out = [a | scale_b * b] along channels   (UpsampleBlock1d.add_skip, unet1d.py:536-537) */
 int adb_cl_concat(const void* a_dev, const void* b_dev, float scale_b, void* out_dev, int64_t rows, int Ca, int Cb, int dtype,
                   void* stream);
+/* WAVenc1d on the tensor cores (W == 2 S, L % W == 0, (W * Cin) % 64 == 0): re-lay the fp32 channels-first input as bf16
+ * channels-last rows [B][L/W + 1][W * Cin] shifted by pad = W/2 - S/2 samples; adb_cl_conv with taps = 2 over these rows and
+ * host-arranged weights [2][W * Cin][2 F] then yields frames (2m, 2m+1) in row m of [B][L/W][2 F] == [B][L/S][F]
+ * (unet1d.py:572-594). */
+int adb_cl_wavenc_prep(const float* x_dev, void* rows_bf16_dev, int B, int Cin, int L, int W, int S, void* stream);
 /* WAVenc1d (unet1d.py:572-594): x [B][Cin][L] fp32 channels-first -> [B][L/S][F] channels-last in `dtype`;
  * WAVdec1d (unet1d.py:596-622): [B][Lc][F] -> y [B][Cout][Lc*S] fp32 channels-first. w in torch layout. */
 int adb_cl_wavenc(const float* x_dev, const float* w_dev, void* out_dev, int B, int Cin, int L, int F, int W, int S, int dtype,
