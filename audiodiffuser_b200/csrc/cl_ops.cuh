@@ -700,16 +700,18 @@ __global__ void __launch_bounds__(256) cl_concat_vec_kernel(const T* __restrict_
     }
 }
 
-// Batched small dense layer with the weights read ONCE for the whole batch: out[b][n] = act(bias[n] + sum_k W[n][k] f(in[b][k])).
-// The (optionally SiLU'd) inputs of up to 32 samples sit transposed in shared memory; lane = sample, one warp per group of
-// CL_LIN_COLS output columns (4 at a time share every staged input value), weight rows loaded coalesced and broadcast
-// with shuffles. grid (ceil(N / (8 * CL_LIN_COLS)), ceil(B / 32)), smem = K * 32 floats; the staging (and its expf) is
-// amortised over 8 * CL_LIN_COLS columns per CTA.
+// Batched small dense layer with the weights read ONCE per 32 samples: out[b][n] = act(bias[n] + sum_k W[n][k] f(in[b][k])).
+// lane = sample: the (optionally SiLU'd) inputs of up to 32 samples sit in shared memory as [32][K + 4] (16-byte loads,
+// conflict-free); one warp owns CL_LIN_COLS output columns at a time and reads their weight rows with warp-uniform 16-byte
+// loads (one broadcast transaction each), so the inner loop is 1 LDS.128 + 8 LDG.128 per 32 FMAs and needs no shuffles.
+// grid (ceil(N / (8 * CL_LIN_COLS)), ceil(B / 32)), smem = 32 * (K + 4) floats; K % 4 == 0 and 16-byte aligned W rows
+// (otherwise the caller uses cl_linear_kernel).
 constexpr int CL_LIN_COLS = 8;
 __global__ void __launch_bounds__(256) cl_linear_batched_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* __restrict__ out, int B, int K,
                                                                 int N, int silu_in, int act) {
-    extern __shared__ float xs[];                   // [K][32]
+    extern __shared__ __align__(16) float xs[];     // [32][K + 4]
+    const int ldx = K + 4;
     const int b0 = blockIdx.y * 32;
     const int nb = min(32, B - b0);
     for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
@@ -719,34 +721,32 @@ __global__ void __launch_bounds__(256) cl_linear_batched_kernel(const float* __r
             v = in[static_cast<long long>(b0 + bb) * K + k];
             if (silu_in) v = v / (1.0f + expf(-v));
         }
-        xs[k * 32 + bb] = v;
+        xs[bb * ldx + k] = v;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nbase = (blockIdx.x * 8 + warp) * CL_LIN_COLS;
-    for (int g = 0; g < CL_LIN_COLS; g += 4) {
-        const int n = nbase + g;
-        if (n >= N) return;
-        const float* wr[4];
+    const int n = (blockIdx.x * 8 + warp) * CL_LIN_COLS;
+    if (n >= N) return;
+    const float4* wr[CL_LIN_COLS];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wr[c] = w + static_cast<long long>(min(n + c, N - 1)) * K;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            float wv[4];
+    for (int c = 0; c < CL_LIN_COLS; ++c) wr[c] = reinterpret_cast<const float4*>(w + static_cast<long long>(min(n + c, N - 1)) * K);
+    const float4* xr = reinterpret_cast<const float4*>(xs + lane * ldx);
+    float acc[CL_LIN_COLS];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) wv[c] = (k0 + lane < K) ? wr[c][k0 + lane] : 0.f;
-            const int kn = min(32, K - k0);
-            for (int j = 0; j < kn; ++j) {
-                const float xv = xs[(k0 + j) * 32 + lane];
+    for (int c = 0; c < CL_LIN_COLS; ++c) acc[c] = 0.f;
+    for (int k4 = 0; k4 < K / 4; ++k4) {            // ascending k per column: same summation order as a scalar loop
+        const float4 xv = xr[k4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c] = fmaf(__shfl_sync(0xffffffffu, wv[c], j), xv, acc[c]);
-            }
+        for (int c = 0; c < CL_LIN_COLS; ++c) {
+            const float4 wv = __ldg(wr[c] + k4);
+            acc[c] = fmaf(wv.x, xv.x, acc[c]); acc[c] = fmaf(wv.y, xv.y, acc[c]);
+            acc[c] = fmaf(wv.z, xv.z, acc[c]); acc[c] = fmaf(wv.w, xv.w, acc[c]);
         }
-        if (lane < nb) {
+    }
+    if (lane < nb) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (n + c < N) out[static_cast<long long>(b0 + lane) * N + n + c] = cl_act(acc[c] + (bias ? bias[n + c] : 0.f), act);
-        }
+        for (int c = 0; c < CL_LIN_COLS; ++c)
+            if (n + c < N) out[static_cast<long long>(b0 + lane) * N + n + c] = cl_act(acc[c] + (bias ? bias[n + c] : 0.f), act);
     }
 }
 
