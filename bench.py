@@ -303,7 +303,7 @@ def run_train(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or (16 if args.precision == "bf16" else 4)
+    B = args.batch or (32 if args.precision == "bf16" else 4)   # 32 = data.batch_size of the reference experiment (diffunet_complex_sc09.yaml:67)
     torch.manual_seed(0)                                   # identical initial weights on every rank, like DDP's broadcast
     net = WaveNetNoise(C, LAYERS, CYCLE, precision=args.precision)
     net.output_projection.conv.weight.data.normal_(0.0, 1.0 / 16.0)
@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 128 UNet1d / 16 train)")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default 256 DiffWave / 128 UNet1d / 32 train)")
     ap.add_argument("--workload", default="diffwave", choices=["diffwave", "unet1d", "train"],
                     help="diffwave = the headline metric (BASELINE.json configs[1]); unet1d = configs[3]")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
