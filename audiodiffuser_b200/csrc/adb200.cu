@@ -347,6 +347,8 @@ struct adb_wavenet {
     float* d_scale = nullptr;         // g / ||v|| per weight-normed conv: [0] input, [1 + 2l] dilated, [2 + 2l] output, [last] skip
     WnJob* d_jobs = nullptr;
     float* wpT = nullptr;             // [layers][512][C] transposed diffusion projections (refold)
+    __nv_bfloat16* wsp_p = nullptr;   // skip projection [C -> C] in cl_conv_tc blocks (training tail on the tensor cores)
+    __nv_bfloat16* wspT_p = nullptr;  // its transpose (dskip = ds2 Wsp)
     const float** fold_tab = nullptr; // 6 x (layers*3) operand pointers of the two batched fold GEMMs (refold)
     float* w1perm = nullptr;          // [3][C][2C] scratch of refold (column-permuted W1)
     std::vector<int64_t> counts, dst_off;   // flat-vector pieces (state_dict order) and their offsets in `params`
@@ -546,6 +548,8 @@ static int refold(adb_wavenet* n) {
             CK(conv_cl_f32(a, 0));
         }
         pack_tc_tail_kernel<<<64, 256>>>(n->wsp_f, n->wsp_tc);
+        cl_pack_conv_tc_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wsp_f, n->wsp_p, C, C, 1);
+        cl_pack_conv_tc_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wspT, n->wspT_p, C, C, 1);
         CK(cudaGetLastError());
         n->tc_ready = true;
     }
@@ -662,6 +666,8 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(dmalloc(n, &n->wtc, static_cast<size_t>(layers) * 32 * 256 * 64));
         CKN(dmalloc(n, &n->wsp_tc, 4ULL * 256 * 64));
         const long long ldm = static_cast<long long>(layers) * 1536;
+        CKN(dmalloc(n, &n->wsp_p, static_cast<size_t>(C) * C));
+        CKN(dmalloc(n, &n->wspT_p, static_cast<size_t>(C) * C));
         CKN(dmalloc(n, &n->mtab, 512ULL * ldm));
         CKN(dmalloc(n, &n->cvec, static_cast<size_t>(ldm)));
         {

@@ -144,10 +144,17 @@ __global__ void permute_gate_cols_kernel(const float* __restrict__ in, const flo
 }
 
 // dst (bf16) = src (fp32)
-__global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        out[i] = __float2bfloat16_rn(in[i]);
+__global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n,
+                                                           float scale = 1.0f) {
+    const long long n4 = n / 4;                                 // n % 4 == 0 and 16-byte aligned buffers at every call site
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(in)[i];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * scale, v.y * scale), hi = __floats2bfloat162_rn(v.z * scale, v.w * scale);
+        uint2 u;
+        u.x = *reinterpret_cast<unsigned*>(&lo); u.y = *reinterpret_cast<unsigned*>(&hi);
+        reinterpret_cast<uint2*>(out)[i] = u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,8 +248,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, f
 // Tail backward (wavenet.py:177-179): F = b_out + sum_c w_out[c] s2[c], s2 = relu(...)
 //   ds2[r][c] = dF[r] w_out[c] [s2 > 0] ; dw_out[c] += sum_r dF[r] s2[r][c] ; db_out += sum_r dF[r]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__ dF, const float* __restrict__ s2,
-                                                       const float* __restrict__ w_out, float* __restrict__ ds2,
+template <typename T>
+__global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__ dF, const T* __restrict__ s2,
+                                                       const float* __restrict__ w_out, T* __restrict__ ds2,
                                                        float* __restrict__ dw_out, float* __restrict__ db_out, long long rows,
                                                        int C) {
     __shared__ float acc_w[1024];
@@ -255,8 +263,8 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__
     float lw = 0.f, lb = 0.f;
     const float wc = w_out[c];
     for (long long r = static_cast<long long>(blockIdx.x) * rstep + rofs; r < rows; r += static_cast<long long>(gridDim.x) * rstep) {
-        const float g = dF[r], s = s2[r * C + c];
-        ds2[r * C + c] = s > 0.f ? g * wc : 0.f;
+        const float g = dF[r], s = cl_ld<T>(s2 + r * C + c);
+        cl_st<T>(ds2 + r * C + c, s > 0.f ? g * wc : 0.f);
         lw = fmaf(g, s, lw);
         if (c == 0) lb += g;
     }
