@@ -12,3 +12,7 @@ echo "ncu launches rc=$?"
 python tools/time_net.py 256 2 1 > gpurun_out/plain_tn.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:wavenet_block -s 2 -c 2 -o gpurun_out/prof_block_$tag python tools/time_net.py 256 2 1 > gpurun_out/ncu_tn.log 2>&1
 echo "ncu full rc=$?"
+python tools/time_step.py > gpurun_out/plain_step.log 2>&1 &&
+ncu --set full --clock-control none -k regex:edm_kernel -s 4 -c 2 -o gpurun_out/prof_step_$tag python tools/time_step.py 67108864 2 > gpurun_out/ncu_step.log 2>&1
+echo "ncu step rc=$?"; cat gpurun_out/plain_step.log
+python bench.py --workload unet1d > gpurun_out/bench_unet_$tag.json 2>> gpurun_out/bench_$tag.err; echo "unet rc=$?"
