@@ -51,6 +51,21 @@ struct ClConvTcParams {
 
 // EPI_WARPS = 4 (192 threads) for the plain / transposed / WAVdec stores; EPI_WARPS = 8 (320 threads) with FUSED = true adds
 // the training step's gate-forward / gate-derivative epilogues, which are epilogue-bound with four warps.
+// One thread's 32-column bf16 chunk of a row = 64 contiguous, 64-byte aligned bytes: two 256-bit accesses.
+__device__ __forceinline__ void ct_store64(__nv_bfloat16* dst, const uint32_t (&v)[16]) {
+    const uint32_t lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+    const uint32_t hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+    stg256(dst, lo);
+    stg256(dst + 16, hi);
+}
+__device__ __forceinline__ void ct_load64(const __nv_bfloat16* src, uint32_t (&v)[16]) {
+    uint32_t lo[8], hi[8];
+    ldg256(src, lo);
+    ldg256(src + 16, hi);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = lo[i]; v[8 + i] = hi[i]; }
+}
+
 template <int EPI_WARPS, bool FUSED>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const ClConvTcParams p) {
@@ -171,16 +186,10 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                         pz[i >> 1] = pack_bf16x2(__fdividef(1.0f, 1.0f + __expf(-g0)) * tanh_fast(f0),
                                                  __fdividef(1.0f, 1.0f + __expf(-g1)) * tanh_fast(f1));
                     }
-                    if (row_ok) {
-                        uint4* yg = reinterpret_cast<uint4*>(yout + grow * a.N + c0);
-                        uint4* yf = reinterpret_cast<uint4*>(yout + grow * a.N + C + c0);
-                        uint4* zo = reinterpret_cast<uint4*>(out + grow * C + c0);
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            yg[m] = make_uint4(pg[4 * m], pg[4 * m + 1], pg[4 * m + 2], pg[4 * m + 3]);
-                            yf[m] = make_uint4(pf[4 * m], pf[4 * m + 1], pf[4 * m + 2], pf[4 * m + 3]);
-                            zo[m] = make_uint4(pz[4 * m], pz[4 * m + 1], pz[4 * m + 2], pz[4 * m + 3]);
-                        }
+                    if (row_ok) {                   // 64 contiguous bytes per destination: two full-sector 256-bit stores each
+                        ct_store64(yout + grow * a.N + c0, pg);
+                        ct_store64(yout + grow * a.N + C + c0, pf);
+                        ct_store64(out + grow * C + c0, pz);
                     }
                 }
             } else if (FUSED && a.mode == CL_MODE_GATE_BWD) {
@@ -194,33 +203,26 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                     tmem_ld_wait();
                     if (!row_ok) continue;
                     const int n = n0 + cc * 32;
-                    const uint4* ygp = reinterpret_cast<const uint4*>(yin + grow * 2 * C + n);
-                    const uint4* yfp = reinterpret_cast<const uint4*>(yin + grow * 2 * C + C + n);
-                    uint4* dg = reinterpret_cast<uint4*>(out + grow * 2 * C + n);
-                    uint4* df = reinterpret_cast<uint4*>(out + grow * 2 * C + C + n);
+                    uint32_t wg[16], wf[16], og[16], of[16];
+                    ct_load64(yin + grow * 2 * C + n, wg);
+                    ct_load64(yin + grow * 2 * C + C + n, wf);
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const uint4 ug = ygp[m], uf = yfp[m];
-                        const uint32_t wg[4] = {ug.x, ug.y, ug.z, ug.w}, wf[4] = {uf.x, uf.y, uf.z, uf.w};
-                        uint32_t og[4], of[4];
+                    for (int e = 0; e < 16; ++e) {
+                        float dgv[2], dfv[2];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float dgv[2], dfv[2];
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const float g = __uint_as_float(h ? (wg[e] & 0xFFFF0000u) : (wg[e] << 16));
-                                const float f = __uint_as_float(h ? (wf[e] & 0xFFFF0000u) : (wf[e] << 16));
-                                const float d = __uint_as_float(r[8 * m + 2 * e + h]);
-                                const float sg = __fdividef(1.0f, 1.0f + __expf(-g)), th = tanh_fast(f);
-                                dgv[h] = d * th * sg * (1.0f - sg);
-                                dfv[h] = d * sg * (1.0f - th * th);
-                            }
-                            og[e] = pack_bf16x2(dgv[0], dgv[1]);
-                            of[e] = pack_bf16x2(dfv[0], dfv[1]);
+                        for (int h = 0; h < 2; ++h) {
+                            const float g = __uint_as_float(h ? (wg[e] & 0xFFFF0000u) : (wg[e] << 16));
+                            const float f = __uint_as_float(h ? (wf[e] & 0xFFFF0000u) : (wf[e] << 16));
+                            const float d = __uint_as_float(r[2 * e + h]);
+                            const float sg = __fdividef(1.0f, 1.0f + __expf(-g)), th = tanh_fast(f);
+                            dgv[h] = d * th * sg * (1.0f - sg);
+                            dfv[h] = d * sg * (1.0f - th * th);
                         }
-                        dg[m] = make_uint4(og[0], og[1], og[2], og[3]);
-                        df[m] = make_uint4(of[0], of[1], of[2], of[3]);
+                        og[e] = pack_bf16x2(dgv[0], dgv[1]);
+                        of[e] = pack_bf16x2(dfv[0], dfv[1]);
                     }
+                    ct_store64(out + grow * 2 * C + n, og);
+                    ct_store64(out + grow * 2 * C + C + n, of);
                 }
             } else
             for (int cc = (nhalf == 2 ? half * ((p.NT / 32 + 1) / 2) : 0); cc < ((nhalf == 2 && !half) ? (p.NT / 32 + 1) / 2 : p.NT / 32); ++cc) {
@@ -259,16 +261,12 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                 if (a.ups == 0) {
                     o = grow * (a.ldo ? a.ldo : a.N) + n;
                     if (res && ok) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res + grow * (a.res_ld ? a.res_ld : a.N) + n);
+                        uint32_t w[16];
+                        ct_load64(res + grow * (a.res_ld ? a.res_ld : a.N) + n, w);
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const uint4 u = rp[m];
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                v[8 * m + 2 * e] += __uint_as_float(w[e] << 16);
-                                v[8 * m + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                            }
+                        for (int e = 0; e < 16; ++e) {
+                            v[2 * e] += __uint_as_float(w[e] << 16);
+                            v[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
                         }
                     }
                     if (a.out_scale != 0.f) {
@@ -282,11 +280,10 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                     o = (static_cast<long long>(b) * a.L_out + to) * cout + c;
                 }
                 if (ok) {
-                    uint4* op = reinterpret_cast<uint4*>(out + o);
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int m = 0; m < 4; ++m)
-                        op[m] = make_uint4(pack_bf16x2(v[8 * m], v[8 * m + 1]), pack_bf16x2(v[8 * m + 2], v[8 * m + 3]),
-                                           pack_bf16x2(v[8 * m + 4], v[8 * m + 5]), pack_bf16x2(v[8 * m + 6], v[8 * m + 7]));
+                    for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+                    ct_store64(out + o, pk);
                 }
             }
             tc_fence_before_sync();
