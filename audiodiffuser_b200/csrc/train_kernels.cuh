@@ -20,17 +20,27 @@ template <typename T>
 __global__ void __launch_bounds__(256) add_bcast_kernel(const T* __restrict__ h, const float* __restrict__ p,
                                                         T* __restrict__ out, int B, int L, int C) {
     constexpr int VE = ClVec<T>::N;
+    constexpr int U = 4;                                   // four independent 16-byte loads in flight per thread
     const int vpr = C / VE;
     const unsigned total = static_cast<unsigned>(B) * L * vpr;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned r = i / vpr, v = i - r * vpr;
-        const unsigned b = r / L;
-        float x[VE];
-        ClVec<T>::load(h + static_cast<size_t>(i) * VE, x);
-        const float* pp = p + static_cast<size_t>(b) * C + v * VE;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        float x[U][VE];
 #pragma unroll
-        for (int k = 0; k < VE; ++k) x[k] += pp[k];
-        ClVec<T>::store(out + static_cast<size_t>(i) * VE, x);
+        for (int u = 0; u < U; ++u) {
+            const unsigned i = i0 + u * stride;
+            if (i < total) ClVec<T>::load(h + static_cast<size_t>(i) * VE, x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned i = i0 + u * stride;
+            if (i >= total) break;
+            const unsigned r = i / vpr, v = i - r * vpr;
+            const float* pp = p + static_cast<size_t>(r / L) * C + v * VE;
+#pragma unroll
+            for (int k = 0; k < VE; ++k) x[u][k] += pp[k];
+            ClVec<T>::store(out + static_cast<size_t>(i) * VE, x[u]);
+        }
     }
 }
 
@@ -231,7 +241,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, f
 #pragma unroll
     for (int k = 0; k < VE; ++k) s[k] = 0.f;
     const T* col = in + static_cast<size_t>(b) * L * ld + v * VE;     // ld = row pitch (>= C)
-    for (int r = r0 + rofs; r < r1; r += rstep) {
+    int r = r0 + rofs;
+    for (; r + 3 * rstep < r1; r += 4 * rstep) {           // four independent 16-byte loads in flight per thread
+        float x[4][VE];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ClVec<T>::load(col + static_cast<size_t>(r + u * rstep) * ld, x[u]);
+#pragma unroll
+        for (int k = 0; k < VE; ++k) s[k] += (x[0][k] + x[1][k]) + (x[2][k] + x[3][k]);
+    }
+    for (; r < r1; r += rstep) {
         float x[VE];
         ClVec<T>::load(col + static_cast<size_t>(r) * ld, x);
 #pragma unroll
