@@ -737,6 +737,7 @@ struct Workspace {
     // bf16 path
     float* E;                            // [B][layers*1536]
     __nv_bfloat16 *hbA, *hbB;
+    __nv_bfloat16* stash;             // [B][L][C] fp16 bits: an even layer's skip term, consumed by the next layer (pair kernel)
     int64_t total;
 };
 
@@ -771,6 +772,7 @@ static Workspace carve(const adb_wavenet* n, int B, int L, int precision, void* 
         w.E = reinterpret_cast<float*>(take(static_cast<int64_t>(B) * n->layers * 1536 * 4));
         w.hbA = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
         w.hbB = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
+        w.stash = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
     }
     w.total = off;
     return w;
@@ -915,6 +917,10 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     const int groups = (num_tiles + cl - 1) / cl;
     const int grid_block = (groups < max_clusters ? groups : max_clusters) * cl;
     __nv_bfloat16 *hin = h_save ? h_save : w.hbA, *hout = (h_save && layers > 1) ? h_save + BL * C : w.hbB;
+    // pair kernel: even layers stash their skip term as fp16, odd layers add it and touch the fp32 sum once for both
+    // (off when per-layer skip sums are dumped for the debug entry point, or with ADB_NO_STASH=1)
+    const bool use_stash = n->pair && dump_layers == 0 && getenv("ADB_NO_STASH") == nullptr;
+    bool skip_written = false;
     for (int l = 0; l < layers; ++l) {
         ScopedTimer t(n, ADB_TIMER_CONV, st);
         CUtensorMap m_h, m_hout, m_skip;
@@ -927,6 +933,9 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
         bp.B = B; bp.L = L; bp.layer = l; bp.layers = layers; bp.dil = 1 << (l % n->cycle);
         bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
         bp.first_layer = (l == 0); bp.write_h = (l + 1 < layers) || (l < dump_layers);
+        bp.add_stash = (use_stash && (l & 1)) ? 1 : 0;
+        if (use_stash && !(l & 1) && l + 1 < layers) bp.skip_mode = 2;
+        else { bp.skip_mode = skip_written ? 0 : 1; skip_written = true; }
         { const char* e = getenv("ADB_DEBUG_FLAGS"); bp.dbg = e ? atoi(e) : 0; }
         bp.cluster = cl;
         if (n->pair) {
@@ -939,10 +948,12 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
             la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
             lc.attrs = la; lc.numAttrs = 1;
             bp.cluster = 2;
-            CUtensorMap m_hout4;
+            CUtensorMap m_hout4, m_stash_ld, m_stash_st;
             rc = get_act_map(n, hout, B, L, 4, &m_hout4);
+            if (!rc) rc = get_act_map(n, w.stash, B, L, 0, &m_stash_ld);
+            if (!rc) rc = get_act_map(n, w.stash, B, L, 4, &m_stash_st);
             if (rc) return rc;
-            CK(cudaLaunchKernelEx(&lc, wavenet_block_pair_kernel, m_h, n->tm_w2, m_skip, m_hout4, bp));
+            CK(cudaLaunchKernelEx(&lc, wavenet_block_pair_kernel, m_h, n->tm_w2, m_skip, m_hout4, m_stash_ld, m_stash_st, bp));
         } else {
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3(grid_block); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = TC_BLOCK_SMEM_BYTES; lc.stream = st;

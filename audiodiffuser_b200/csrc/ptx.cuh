@@ -334,6 +334,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// same, saturating to +-65504 instead of overflowing to infinity
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 // MUFU tanh on two fp16 values at once (max rel. error ~2^-11): halves the SFU work of the gate
 __device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
     uint32_t y;

@@ -75,6 +75,9 @@ struct BlockTcParams {
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
     int dbg;                        // debug bits (ADB_DEBUG_FLAGS): 1 = skip epilogue-2 global memory traffic
     int cluster;                    // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across the cluster
+    // pair kernel only — the fp32 skip sum is read-modify-written every SECOND layer:
+    int skip_mode;                  // 0: skip += value (TMA reduce-add)  1: skip = value  2: stash the value as bf16 for the next layer
+    int add_stash;                  // 1: the previous layer's stashed skip contribution is added to this layer's (identity MMA)
 };
 
 // Optional in-kernel cycle accounting (BlockTcParams::dbg & 2): where each role waits.

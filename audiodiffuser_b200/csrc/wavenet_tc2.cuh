@@ -9,6 +9,12 @@
 //   * TMA completions of both CTAs are counted on rank 0's "full" barrier; tcgen05.commit multicasts the
 //     "stage free" / "accumulator ready" arrivals to both CTAs; both CTAs' epilogue warps arrive on rank 0's
 //     "accumulator drained" / "z ready" barriers.
+// Skip accumulation (wavenet.py:145-149) touches the fp32 running sum only every second layer: an even layer writes its
+// skip contribution as fp16 into a stash buffer (2 bytes per element, plain TMA store), the following odd layer loads that
+// tile through TMA and adds it to its own accumulator with the same identity-MMA trick that adds the residual input
+// (exact: fp16 x 1.0 accumulated in fp32), then does ONE fp32 reduce-add for both layers. HBM traffic per pair of layers
+// drops from 2 x 8 bytes of read-modify-write per skip element to 8 + 2 + 2, and the L2 reductions are halved. The stashed
+// contribution is rounded to fp16 once (relative 2^-12 of one layer's skip term; saturating at +-65504).
 #pragma once
 #include "wavenet_tc.cuh"
 
@@ -25,7 +31,8 @@ struct Tc2Smem {
     static constexpr int z = T2_STAGES * T2_STAGE_BYTES;            // 64 KB gated activations (GEMM2 A operand)
     static constexpr int stg = z + TC_Z_BYTES;                      // 8 x 2 KB
     static constexpr int ident = stg + 8 * T2_STG_BYTES;            // [32 n][64 k] bf16 half identity (4 KB)
-    static constexpr int evec = ident + 32 * 128;                   // 3 x 512 fp32
+    static constexpr int ident16 = ident + 32 * 128;                // the same identity in fp16 (for the fp16 skip stash)
+    static constexpr int evec = ident16 + 32 * 128;                 // 3 x 512 fp32
     static constexpr int esum = evec + 3 * 512 * 4;                 // 512 fp32
     static constexpr int b2 = esum + 512 * 4;                       // 512 fp32
     static constexpr int bars = b2 + 512 * 4;
@@ -39,6 +46,7 @@ constexpr int TC2_SMEM_BYTES = Tc2Smem::total;
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                           const __grid_constant__ CUtensorMap tm_skip, const __grid_constant__ CUtensorMap tm_hout,
+                          const __grid_constant__ CUtensorMap tm_stash_ld, const __grid_constant__ CUtensorMap tm_stash_st,
                           const BlockTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_evec = reinterpret_cast<float*>(smem + Tc2Smem::evec);
@@ -62,6 +70,8 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
         tma_prefetch_desc(&tm_w);
         tma_prefetch_desc(&tm_skip);
         tma_prefetch_desc(&tm_hout);
+        tma_prefetch_desc(&tm_stash_ld);
+        tma_prefetch_desc(&tm_stash_st);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -82,16 +92,19 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
         // this CTA's half of the 64 x 64 identity: local row i is n = 32 rank + i; element (n, k = n) sits in
         // 16-byte chunk (n / 8) ^ (i & 7) of row i (128-byte swizzle)
         uint4* id4 = reinterpret_cast<uint4*>(smem + Tc2Smem::ident);
+        uint4* id16 = reinterpret_cast<uint4*>(smem + Tc2Smem::ident16);
         for (int i = threadIdx.x - 64; i < 32 * 8; i += TC_EPI_THREADS) {
             const int r = i >> 3, phys = i & 7;
             const int n = 32 * rank + r;
             const int chunk = phys ^ (r & 7);
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            uint32_t w[4] = {0u, 0u, 0u, 0u}, w16[4] = {0u, 0u, 0u, 0u};
             if (chunk == (n >> 3)) {
                 const int e = n & 7;
                 w[e >> 1] = (e & 1) ? 0x3F800000u : 0x00003F80u;
+                w16[e >> 1] = (e & 1) ? 0x3C000000u : 0x00003C00u;
             }
             id4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            id16[i] = make_uint4(w16[0], w16[1], w16[2], w16[3]);
         }
         fence_proxy_async_smem();
     }
@@ -103,6 +116,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
     constexpr uint32_t IDESC = umma_idesc_pair_bf16(256);
     constexpr uint32_t IDESC_N64 = umma_idesc_pair_bf16(64);
     constexpr uint32_t IDESC_F16 = umma_idesc_pair_f16(256);
+    constexpr uint32_t IDESC_N64_F16 = umma_idesc_pair_f16(64);
 
     const int pair_id = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
@@ -135,7 +149,8 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                         uint8_t* sb = sa + T2_A_BYTES;
                         const int wblk = p.layer * TC_W_BLOCKS_PER_LAYER +
                                          (job < 2 ? job * 12 + kb : 24 + (job - 2) * 4 + kb);
-                        const uint32_t bytes = job <= 2 ? T2_STAGE_BYTES : T2_B_BYTES;
+                        const bool ident_job = job == 2 || (job == 3 && p.add_stash);            // the A slot carries a tile for the identity MMA
+                        const uint32_t bytes = (job < 2 || ident_job) ? T2_STAGE_BYTES : T2_B_BYTES;
                         if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * bytes);   // both CTAs' bytes
                         else        mbar_arrive_cluster(&bar_full[stage], 0);
                         if (job < 2) {
@@ -143,6 +158,8 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                             tma_load_3d_pair(sa, &tm_h, &bar_full[stage], cib * 64, t0 + (tap - 1) * p.dil, b);
                         } else if (job == 2) {
                             tma_load_3d_pair(sa, &tm_h, &bar_full[stage], kb * 64, t0, b);   // h for the identity MMA
+                        } else if (p.add_stash) {
+                            tma_load_3d_pair(sa, &tm_stash_ld, &bar_full[stage], kb * 64, t0, b);   // previous layer's skip term
                         }
                         tma_load_2d_pair(sb, &tm_w, &bar_full[stage], 0, wblk * 256 + rank * 128);
                     }
@@ -161,6 +178,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
             uint32_t it = 0;
             const uint32_t z_addr = smem_u32(smem + Tc2Smem::z);
             const uint32_t id_addr = smem_u32(smem + Tc2Smem::ident);
+            const uint32_t id16_addr = smem_u32(smem + Tc2Smem::ident16);
             long long dbg_acc[16] = {};
             TC_DBG_T0(tm_all);
             for (int grp = pair_id; grp < num_groups; grp += num_pairs, ++it) {
@@ -205,6 +223,12 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                                 for (int k = 0; k < 4; ++k)
                                     umma_bf16_ss_pair(d_tmem + kb * 64, umma_desc_sw128_kmajor(sa + k * 32),
                                                       umma_desc_sw128_kmajor(id_addr + k * 32), IDESC_N64, 1u);
+                            } else if (job == 3 && p.add_stash) {
+                                // + the previous layer's stashed skip term (fp16 x 1.0 in fp32)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_ss_pair(d_tmem + kb * 64, umma_desc_sw128_kmajor(sa + k * 32),
+                                                      umma_desc_sw128_kmajor(id16_addr + k * 32), IDESC_N64_F16, 1u);
                             }
                             umma_commit_pair_mc(&bar_empty[stage], 3);           // stage free in both CTAs
                             if (kb == nkb - 1) umma_commit_pair_mc(&bar_tfull[buf], 3);   // accumulator ready in both CTAs
@@ -397,9 +421,29 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                     uint32_t r[32];
                     tmem_ld_32x32(t_lane + 256 + col, r);
                     tmem_ld_wait();
-                    uint8_t* brow = stg + (cc & 1) * 4096 + lane * 128;
+                    uint8_t* cbuf = stg + (cc & 1) * 4096;
                     if (lane == 0) tma_store_wait_read<1>();
                     __syncwarp();
+                    if (p.skip_mode == 2) {
+                        // stash: this layer's skip term leaves as fp16 (32 rows x 64 bytes, 64-byte swizzle) for the next layer
+                        const int sw_w = (lane >> 1) & 3;
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2)
+                            pk[i >> 1] = pack_f16x2_sat(__uint_as_float(r[i]) + s_b2[256 + col + i], __uint_as_float(r[i + 1]) + s_b2[256 + col + i + 1]);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            *reinterpret_cast<uint4*>(cbuf + lane * 64 + ((m ^ sw_w) << 4)) =
+                                make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && tile_valid && !(p.dbg & 33)) {
+                            tma_store_3d(&tm_stash_st, cbuf, col, trow, b);
+                            tma_store_commit();
+                        }
+                        continue;
+                    }
+                    uint8_t* brow = cbuf + lane * 128;
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
                         float4 v;
@@ -413,8 +457,8 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0 && tile_valid && !(p.dbg & 33)) {
-                        if (p.first_layer) tma_store_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
-                        else               tma_reduce_add_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
+                        if (p.skip_mode == 1) tma_store_3d(&tm_skip, cbuf, col, trow, b);
+                        else                  tma_reduce_add_3d(&tm_skip, cbuf, col, trow, b);
                         tma_store_commit();
                     }
                 }

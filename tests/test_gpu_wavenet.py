@@ -189,7 +189,14 @@ def test_pair_kernel_vs_reference_golden(dev, name, monkeypatch):
     monkeypatch.setenv("ADB_TC_PAIR", "0")
     base = make_net(C, layers, cycle, seed, "bf16", dev)(audio, t)
     monkeypatch.setenv("ADB_TC_PAIR", "1")
+    monkeypatch.setenv("ADB_NO_STASH", "1")                    # fp32 skip read-modify-write in every layer
+    plain = make_net(C, layers, cycle, seed, "bf16", dev)(audio, t)
+    monkeypatch.delenv("ADB_NO_STASH")                         # default: even layers stash their skip term as fp16
     out = make_net(C, layers, cycle, seed, "bf16", dev)(audio, t)
     N.check_async()
+    assert rel_l2(plain, base) < 1e-6
     assert rel_l2(out, g["out"]) < TOL["bf16"], rel_l2(out, g["out"])
-    assert rel_l2(out, base) < 1e-6
+    assert rel_l2(plain, g["out"]) < TOL["bf16"]
+    # one fp16 rounding of every second layer's skip term: far below the bf16 operand error itself
+    assert rel_l2(out, plain) < 3e-3, rel_l2(out, plain)
+    assert rel_l2(out, g["out"]) < 1.05 * rel_l2(plain, g["out"]) + 1e-4            # and it does not move the error against the reference
