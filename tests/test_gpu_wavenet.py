@@ -200,3 +200,27 @@ def test_pair_kernel_vs_reference_golden(dev, name, monkeypatch):
     # one fp16 rounding of every second layer's skip term: far below the bf16 operand error itself
     assert rel_l2(out, plain) < 3e-3, rel_l2(out, plain)
     assert rel_l2(out, g["out"]) < 1.05 * rel_l2(plain, g["out"]) + 1e-4            # and it does not move the error against the reference
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_debug_per_block_outputs_vs_oracle(dev, precision):
+    """adb_wavenet_forward_debug: the residual stream h and the running skip sum after every block against the oracle's
+    intermediates on the same seeded inputs (the skip stash is switched off on this entry point, so every running sum
+    is complete)."""
+    from oracle import wavenet as owav
+    from oracle.weights import make_wavenet_state_dict
+    C, layers, cycle, seed, B, L = 256, 4, 3, 31, 2, 700
+    sd = make_wavenet_state_dict(C, layers, seed)
+    audio = torch.randn(B, L, generator=torch.Generator().manual_seed(seed + 1))
+    t = torch.tensor([-0.4, 0.9])
+    with torch.no_grad():
+        want, inter = owav.wavenet_forward(sd, audio, t, cycle, return_intermediates=True)
+    net = make_net(C, layers, cycle, seed, precision, dev)
+    out, dh, ds = net.forward_debug(audio.to(dev), t.to(dev), layers)
+    tol = TOL[precision]
+    assert rel_l2(out, want) < tol
+    for n in range(layers):
+        if n + 1 < layers:                                           # the last block's residual output is never computed
+            assert rel_l2(dh[n].transpose(1, 2), inter[f"h{n}"]) < tol, (n, "h")
+        assert rel_l2(ds[n].transpose(1, 2), inter[f"skip{n}"]) < tol, (n, "skip")
+    assert rel_l2(out, net(audio.to(dev), t.to(dev))) < (1e-6 if precision == "fp32" else 3e-3)   # same result as the plain entry
