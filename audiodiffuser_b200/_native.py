@@ -65,6 +65,7 @@ _SIGS = {
     "adb_cl_pack_conv_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "adb_cl_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "adb_cl_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_cast": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "adb_cl_label_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "adb_cl_time_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "adb_cl_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -312,6 +312,9 @@ class UNet1dBase(nn.Module):
             wc[1, :S * cin_w, nf:] = wk[S * cin_w:]               # ... and first half of row m+1
             P["to_in.tc"] = gemm_weight(wc, None, dict(off0=0, dil=1, ups=0))
         P["cond_w"] = torch.cat(cond_w, dim=0).contiguous()
+        if bf16 and P["cond_w"].shape[0] % 64 == 0 and P["cond_w"].shape[1] % 64 == 0:
+            # all (scale, shift) projections as one tensor-core GEMM [B][T] x [T][sum 2C] (bias in the epilogue)
+            P["cond_tc"] = gemm_weight(P["cond_w"].t().unsqueeze(0), torch.cat(cond_b, dim=0), dict(off0=0, dil=1, ups=0))
         P["cond_b"] = torch.cat(cond_b, dim=0).contiguous()
         P["cond_off"] = cond_off
         P["lc"] = lc
@@ -412,8 +415,17 @@ class UNet1dBase(nn.Module):
             cond = torch.empty(B, T + cd, dtype=torch.float32, device=dev)
             N.check(lib.adb_cl_concat(N.ptr(temb), N.ptr(e3), 1.0, N.ptr(cond), B, T, cd, 0, st))
         ss_all = torch.empty(B, P["cond_w"].shape[0], dtype=torch.float32, device=dev)
-        N.check(lib.adb_cl_linear(N.ptr(cond), N.ptr(P["cond_w"]), N.ptr(P["cond_b"]), N.ptr(ss_all), B, cond.shape[1], ss_all.shape[1],
-                                  1, ACT_NONE, st))
+        if "cond_tc" in P:
+            ent, Tc, Nc = P["cond_tc"], cond.shape[1], ss_all.shape[1]
+            cond_b16 = torch.empty(B, Tc, dtype=torch.bfloat16, device=dev)
+            N.check(lib.adb_cl_cast(N.ptr(cond), N.ptr(cond_b16), B * Tc, 1, 1, st))
+            ss_b16 = torch.empty(B, Nc, dtype=torch.bfloat16, device=dev)
+            N.check(lib.adb_cl_conv(N.ptr(cond_b16), N.ptr(ent["w"]), N.ptr(ent["bias"]), N.ptr(None), N.ptr(ss_b16), 1, B, B, Tc, Nc,
+                                    1, 0, 1, ACT_NONE, 0, 0, 0, dt, st))
+            N.check(lib.adb_cl_cast(N.ptr(ss_b16), N.ptr(ss_all), B * Nc, 0, 0, st))
+        else:
+            N.check(lib.adb_cl_linear(N.ptr(cond), N.ptr(P["cond_w"]), N.ptr(P["cond_b"]), N.ptr(ss_all), B, cond.shape[1],
+                                      ss_all.shape[1], 1, ACT_NONE, st))
 
         # input transform (WAVenc1d, unet1d.py:572-594)
         nf = cfg["num_filters"]

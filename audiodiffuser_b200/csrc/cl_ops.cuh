@@ -196,6 +196,21 @@ __global__ void cl_time_features_kernel(const float* __restrict__ t, const float
     out[i] = (j - 1 < half) ? sinf(f) : cosf(f);
 }
 
+// fp32 -> bf16 with an optional SiLU (the operand of the conditioning GEMM, unet1d.py:279-283), and bf16 -> fp32
+__global__ void cl_cast_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n, int silu) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float v = in[i];
+        if (silu) v = v / (1.0f + expf(-v));
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+__global__ void cl_cast_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = __bfloat162float(in[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupNorm (nn.GroupNorm(num_groups, C), unet1d.py:179) over (C/G channels x L) per sample.
 //   pass 1: fp64 sum / sum of squares per (b, g) -> sums[b][g][2] (zeroed by the caller)

@@ -209,6 +209,11 @@ int adb_cl_linear(const float* in_dev, const float* w_dev, const float* bias_dev
                   int silu_in, int act, void* stream);
 /* LabelEmbedder lookup with classifier-free-guidance dropout (conditioner.py:94-106): out[b] = drop[b] ? null_row :
  * table[labels[b]] (labels int64 [B]; drop int32 [B] or NULL = keep all); fp32 [B][C] */
+/* to_bf16 != 0: out_bf16[i] = bf16(silu ? SiLU(in_f32[i]) : in_f32[i]); to_bf16 == 0: out_f32[i] = float(in_bf16[i]). The
+ * operand / result conversions around the tensor-core form of the per-block conditioning projections
+ * (`to_cond_embedding` = SiLU -> Linear, unet1d.py:279-283, :304-310), which in bf16 mode run as ONE adb_cl_conv over
+ * [1][B][T] instead of the fp32 adb_cl_linear. */
+int adb_cl_cast(const void* in_dev, void* out_dev, int64_t n, int to_bf16, int silu, void* stream);
 int adb_cl_label_embed(const float* table_dev, const float* null_row_dev, const long long* labels_dev, const int* drop_dev,
                        float* out_dev, int B, int C, int num_classes, void* stream);
 /* [t, sin(2 pi t w), cos(2 pi t w)] -> out [B][2*half+1]   (LearnedPositionalEmbedding, unet1d.py:128-142) */
