@@ -484,7 +484,7 @@ static int make_act_map(CUtensorMap* map, const void* base, int B, int L, int ki
 static int get_act_map(adb_wavenet* n, const void* ptr, int B, int L, int kind, CUtensorMap* out) {
     for (auto& m : n->hmaps)
         if (m.ptr == ptr && m.B == B && m.L == L && m.kind == kind) { *out = m.map; return ADB_OK; }
-    if (n->hmaps.size() > 64) n->hmaps.clear();
+    if (n->hmaps.size() > 512) n->hmaps.clear();       // training keeps one activation buffer per block: ~150 maps
     HMap m;
     m.ptr = ptr; m.B = B; m.L = L; m.kind = kind;
     int rc = make_act_map(&m.map, ptr, B, L, kind);
