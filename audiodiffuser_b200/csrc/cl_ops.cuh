@@ -400,6 +400,120 @@ __global__ void __launch_bounds__(256) cl_attention_kernel(const T* __restrict__
     }
 }
 
+// Self-attention core on the tensor cores (bf16 activations, head dimension 64, L % 16 == 0, L <= 128 — the U-Net's
+// attention levels): one CTA per (batch, head), K as [L][64 + 8] and V transposed as [64][L + 8] in shared memory (both
+// paddings make the mma fragment loads bank-conflict free), one warp per 16 query rows. S = Q K^T and O = P V are
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate); the whole score row block (16 x L) lives in registers, softmax in fp32,
+// P rounded to bf16 for the second product exactly like `attn.to(sim.dtype)` (attention_utils.py:178-179).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t att_pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr int ATT_D = 64, ATT_LMAX = 128, ATT_KPAD = 8, ATT_VPAD = 8;
+__global__ void __launch_bounds__(256) cl_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                                                               __nv_bfloat16* __restrict__ out, int L, int C, int heads) {
+    extern __shared__ __align__(16) uint8_t smem_att_mma[];
+    constexpr int LDK = ATT_D + ATT_KPAD;                      // 72 bf16 = 144 bytes per key row
+    const int ldv = L + ATT_VPAD;                              // bf16 per row of V^T
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att_mma);                  // [L][LDK]
+    __nv_bfloat16* Vt = Ks + static_cast<size_t>(L) * LDK;                               // [64][ldv]
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const __nv_bfloat16* kvb = kv + static_cast<long long>(b) * L * 2 * C + h * ATT_D;
+    for (int i = threadIdx.x; i < L * (ATT_D / 8); i += blockDim.x) {          // 16-byte pieces: 8 per key row
+        const int r = i >> 3, c8 = (i & 7) * 8;
+        const uint4 kk = *reinterpret_cast<const uint4*>(kvb + static_cast<long long>(r) * 2 * C + c8);
+        *reinterpret_cast<uint4*>(Ks + r * LDK + c8) = kk;
+        const uint4 vv = *reinterpret_cast<const uint4*>(kvb + static_cast<long long>(r) * 2 * C + C + c8);
+        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Vt[(c8 + e) * ldv + r] = ve[e];
+    }
+    __syncthreads();
+    const int g = lane >> 2, tig = lane & 3;
+    const int nblk = L >> 3;                                   // key blocks of 8
+    const float scale = 0.125f;                                // 64^-1/2
+    for (int q0 = warp * 16; q0 < L; q0 += nwarps * 16) {
+        const __nv_bfloat16* q_lo = q + (static_cast<long long>(b) * L + q0 + g) * C + h * ATT_D;
+        const __nv_bfloat16* q_hi = q_lo + 8LL * C;
+        uint32_t qa[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(q_lo + ks * 16 + 2 * tig);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(q_hi + ks * 16 + 2 * tig);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(q_lo + ks * 16 + 8 + 2 * tig);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(q_hi + ks * 16 + 8 + 2 * tig);
+        }
+        float sc[ATT_LMAX / 8][4];
+#pragma unroll
+        for (int nb = 0; nb < ATT_LMAX / 8; ++nb) {
+            sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
+            if (nb < nblk) {
+                const __nv_bfloat16* krow = Ks + (nb * 8 + g) * LDK + 2 * tig;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_bf16_16816(sc[nb], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3],
+                                   *reinterpret_cast<const uint32_t*>(krow + ks * 16), *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8));
+            }
+        }
+        // softmax over the keys of rows q0 + g (values [.][0..1]) and q0 + g + 8 (values [.][2..3])
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < ATT_LMAX / 8; ++nb)
+            if (nb < nblk) {
+                sc[nb][0] *= scale; sc[nb][1] *= scale; sc[nb][2] *= scale; sc[nb][3] *= scale;
+                m0 = fmaxf(m0, fmaxf(sc[nb][0], sc[nb][1]));
+                m1 = fmaxf(m1, fmaxf(sc[nb][2], sc[nb][3]));
+            }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < ATT_LMAX / 8; ++nb)
+            if (nb < nblk) {
+                sc[nb][0] = expf(sc[nb][0] - m0); sc[nb][1] = expf(sc[nb][1] - m0);
+                sc[nb][2] = expf(sc[nb][2] - m1); sc[nb][3] = expf(sc[nb][3] - m1);
+                l0 += sc[nb][0] + sc[nb][1];
+                l1 += sc[nb][2] + sc[nb][3];
+            }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+        // O = P V with the normalised probabilities rounded to bf16 (the accumulator layout of S is the A layout of P)
+        float oc[ATT_D / 8][4];
+#pragma unroll
+        for (int nb = 0; nb < ATT_D / 8; ++nb) oc[nb][0] = oc[nb][1] = oc[nb][2] = oc[nb][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < ATT_LMAX / 16; ++kk) {
+            if (kk < (L >> 4)) {
+                const uint32_t a0 = att_pack_bf16(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0);
+                const uint32_t a1 = att_pack_bf16(sc[2 * kk][2] * inv1, sc[2 * kk][3] * inv1);
+                const uint32_t a2 = att_pack_bf16(sc[2 * kk + 1][0] * inv0, sc[2 * kk + 1][1] * inv0);
+                const uint32_t a3 = att_pack_bf16(sc[2 * kk + 1][2] * inv1, sc[2 * kk + 1][3] * inv1);
+#pragma unroll
+                for (int nb = 0; nb < ATT_D / 8; ++nb) {
+                    const __nv_bfloat16* vrow = Vt + (nb * 8 + g) * ldv + kk * 16 + 2 * tig;
+                    mma_bf16_16816(oc[nb], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(vrow),
+                                   *reinterpret_cast<const uint32_t*>(vrow + 8));
+                }
+            }
+        }
+        __nv_bfloat16* o_lo = out + (static_cast<long long>(b) * L + q0 + g) * C + h * ATT_D;
+        __nv_bfloat16* o_hi = o_lo + 8LL * C;
+#pragma unroll
+        for (int nb = 0; nb < ATT_D / 8; ++nb) {
+            *reinterpret_cast<uint32_t*>(o_lo + nb * 8 + 2 * tig) = att_pack_bf16(oc[nb][0], oc[nb][1]);
+            *reinterpret_cast<uint32_t*>(o_hi + nb * 8 + 2 * tig) = att_pack_bf16(oc[nb][2], oc[nb][3]);
+        }
+    }
+}
+
 // out[r][0:Ca] = a[r][:], out[r][Ca:Ca+Cb] = b[r][:] * scale_b   (UpsampleBlock1d.add_skip, unet1d.py:536-537)
 template <typename T>
 __global__ void __launch_bounds__(256) cl_concat_kernel(const T* __restrict__ a, const T* __restrict__ bsrc, float scale_b,

@@ -116,3 +116,35 @@ def test_unet_class_conditioning_and_cfg(dev, precision):
     N.check_async()
     with pytest.raises(NotImplementedError):
         net(x, t, classes=cls, cond_drop_prob=0.3)
+
+
+@pytest.mark.parametrize("L", [16, 32, 64, 128, 24])
+def test_attention_kernels_vs_fp64_softmax_attention(dev, L, monkeypatch):
+    """adb_cl_attention (attention_utils.py:163-184) at the U-Net's head dimension 64: the mma.sync tensor-core kernel
+    (L % 16 == 0, L <= 128), the CUDA-core kernel it falls back to (L = 24; ADB_NO_MMA_ATTENTION) and the fp32 kernel,
+    against softmax(q k^T / 8) v evaluated in fp64 on the same bf16-rounded inputs."""
+    from audiodiffuser_b200 import _native as N
+    lib, st = N.lib(), N.stream_ptr(dev)
+    B, heads, d = 3, 8, 64
+    C = heads * d
+    gen = torch.Generator().manual_seed(L)
+    q = torch.randn(B, L, C, generator=gen).to(dev).to(torch.bfloat16)
+    kv = (torch.randn(B, L, 2 * C, generator=gen) * 1.5).to(dev).to(torch.bfloat16)
+    qd, kd, vd = q.double(), kv[..., :C].double(), kv[..., C:].double()
+    split = lambda a: a.reshape(B, L, heads, d).transpose(1, 2)            # noqa: E731
+    p = torch.softmax(split(qd) @ split(kd).transpose(-1, -2) / 8.0, dim=-1)
+    want = (p @ split(vd)).transpose(1, 2).reshape(B, L, C)
+
+    def run(dtype_id, qq, kk):
+        o = torch.empty_like(qq)
+        N.check(lib.adb_cl_attention(N.ptr(qq), N.ptr(kk), N.ptr(o), B, L, C, heads, dtype_id, st))
+        N.check_async()
+        return o
+
+    got = run(1, q, kv)                                                    # bf16: mma kernel when L % 16 == 0
+    assert rel_l2(got, want) < 6e-3, rel_l2(got, want)
+    monkeypatch.setenv("ADB_NO_MMA_ATTENTION", "1")
+    ref = run(1, q, kv)                                                    # bf16 CUDA-core kernel
+    assert rel_l2(ref, want) < 4e-3
+    assert rel_l2(got, ref) < 6e-3
+    assert rel_l2(run(0, q.float(), kv.float()), want) < 1e-5              # fp32 kernel
