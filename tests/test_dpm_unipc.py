@@ -55,6 +55,43 @@ def test_order_schedule_and_constructor_conventions():
         DPMSampler(1.0, num_steps=4)(torch.zeros(1, 1, 8), fn=None, net=None, sigmas=_schedule(5))
 
 
+def test_host_coefficient_folding_on_cpu(monkeypatch):
+    """The solvers' host logic — time grid, phi-functions, UniPC solves, history shifts, folding of every update into
+    `a x + sum c_k m_k` — without a GPU: the one-launch update and the device checks are replaced by torch stand-ins, the
+    denoiser is the oracle's. Every golden case must come out (the scalars are folded in double precision)."""
+    from audiodiffuser_b200 import _native as N
+    from audiodiffuser_b200.components import sampler_dpm
+    from oracle import edm, wavenet as owav
+    from oracle.weights import make_wavenet_state_dict
+
+    def lincomb_cpu(x, a, terms, clamp=False):
+        assert len(terms) <= 4                                             # what one adb_edm_lincomb_n launch can take
+        out = float(a) * x.double()
+        for c, m in terms:
+            out = out + float(c) * m.double()
+        out = out.float()
+        return out.clamp(-1.0, 1.0) if clamp else out
+
+    monkeypatch.setattr(sampler_dpm, "lincomb", lincomb_cpu)
+    monkeypatch.setattr(N, "require_cuda_f32", lambda t, name: t)
+    monkeypatch.setattr(N, "ensure_device", lambda d: None)
+    g = load_golden("dpm_unipc_small")
+    C, layers, cycle, B, L, seed = (int(v) for v in g["cfg"])
+    net_fn = owav.make_net_fn(make_wavenet_state_dict(C, layers, seed), cycle)
+    fn = lambda x, net, sigma, inference, cond_scale, **kw: edm.denoise(x, net, 0.2, sigma=sigma)      # noqa: E731
+    noise = torch.from_numpy(g["noise"])
+    for name, kw, points in DPM_CASES:
+        smp = sampler_dpm.DPMSampler(cond_scale=1.0, **kw)
+        out = smp(noise, fn=fn, net=net_fn, sigmas=_schedule(points))
+        assert rel_l2(out, g["dpm_" + name]) < 3e-6, (name, rel_l2(out, g["dpm_" + name]))
+        assert smp.last_nfe == int(g["nfe_dpm_" + name]), name
+    for name, kw, points in UNIPC_CASES:
+        smp = sampler_dpm.UniPCSampler(cond_scale=1.0, **kw)
+        out = smp(noise, fn=fn, net=net_fn, sigmas=_schedule(points))
+        assert rel_l2(out, g["unipc_" + name]) < 3e-6, (name, rel_l2(out, g["unipc_" + name]))
+        assert smp.last_nfe == int(g["nfe_unipc_" + name]), name
+
+
 def _gpu_net(g, dev, precision="fp32"):
     from audiodiffuser_b200.backbones.wavenet import WaveNetNoise
     from audiodiffuser_b200.components.diffusion import EluDiffusion
