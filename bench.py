@@ -266,7 +266,7 @@ def run_unet(args, rank, world, local_rank):
                 "gpu_launches": int(launches), "effective_tflops": UNET_FLOP_EVAL * nfe * total / (ms_res * 1e-3) / 1e12,
                 "ms_per_network_evaluation": ms_res / args.steps / nfe, "clocks": clk}
         peaks = load_peaks()
-        line["roofline"] = {"bound": "tensor", "kernel": "whole network evaluation (cl_conv_tc_kernel is about two thirds of it at B=128; 57 % in profiles/r1_launches_unet1d_b128.csv, captured before attention moved to mma.sync)",
+        line["roofline"] = {"bound": "tensor", "kernel": "whole network evaluation (cl_conv_tc_kernel is 62 % of it at B=128, GroupNorm 24 %, profiles/r1_launches_unet1d_b128.csv)",
                             "achieved": line["effective_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": line["effective_tflops"] / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"]}
         if not args.no_cpu_baseline and world == 1:       # host baseline: rank 0 at N = 1 only
