@@ -128,7 +128,9 @@ def step_kernel_hbm(dev, elements=64 * 1024 * 1024, reps=6):
             "avg_ms": ms / (2 * reps), "elements": elements}
 
 
-CPU_BATCH = 8        # BASELINE.json configs[0]: the reference's CPU-runnable case is batch 8
+# BASELINE.json configs[0]: the reference's CPU-runnable case is batch 8 (ADB_BENCH_CPU_BATCH shrinks the sample for the
+# contract test of this arm, tests/test_bench_contract.py)
+CPU_BATCH = int(os.environ.get("ADB_BENCH_CPU_BATCH", "8"))
 
 
 def cpu_reference_eval_time(n_evals, threads):
