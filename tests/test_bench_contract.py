@@ -26,3 +26,26 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_one_contract_line():
+    """The product arm at a small batch: one JSON line with the roofline / e2e / clocks / launch-count keys, measured on the
+    device (kernel launches > 0, e2e with host buffers, no CPU fallback)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--batch", "8", "--steps", "1", "--warmup", "3",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in [k for k in REQUIRED if k not in ("impl", "cpu_baseline")] + ["roofline", "clocks"]:
+        assert k in d, k
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["dtype"] == "bf16" and d["scaling"] == "weak"
+    assert d["gpu_launches"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 8 * 16000 * 4 == d["e2e"]["d2h_bytes_per_step"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
