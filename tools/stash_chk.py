@@ -1,5 +1,7 @@
+"""Pair kernel: outputs with the fp16 skip stash (default) against ADB_NO_STASH=1 and against the reference goldens."""
 import os, sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_golden, rel_l2
 from audiodiffuser_b200 import WaveNetNoise, _native as N
 from oracle.weights import make_wavenet_state_dict
