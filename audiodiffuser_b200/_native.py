@@ -11,12 +11,13 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, POINTE
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadb200.so")
+# tools/ may select the -DADB_DEBUG build (cycle accounting) with ADB_LIB=debug; everything else loads the product library
+LIB_PATH = os.path.join(_HERE, "libadb200_dbg.so" if os.environ.get("ADB_LIB") == "debug" else "libadb200.so")
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16}
-TIMER_NAMES = ("conv", "step", "aux", "tail")
+TIMER_NAMES = ("conv", "step", "aux", "tail", "skip")
 
 _lib = None
 

@@ -19,6 +19,7 @@
 #include "wavenet_f32.cuh"
 #include "wavenet_tc.cuh"
 #include "wavenet_tc2.cuh"
+#include "wavenet_tc3.cuh"
 #include "cl_ops.cuh"
 #include "cl_conv_tc.cuh"
 #include "train_kernels.cuh"
@@ -360,8 +361,19 @@ struct adb_wavenet {
     float* mtab = nullptr;            // [512][layers*3*512]  (W1[tap] Wp)^T
     float* cvec = nullptr;            // [layers*3*512]       W1[tap] bp (+ b1 for the centre tap)
     CUtensorMap tm_w, tm_w2, tm_w4, tm_wsp;     // weight maps with box rows 256 / 128 / 64 (cluster 1 / 2 / 4)
-    int cluster = 2;                            // CTAs per cluster for the residual-block kernel (ADB_TC_CLUSTER)
-    int pair = 1;                               // 1: CTA-pair (cta_group::2) residual-block kernel (ADB_TC_PAIR=0: single-CTA kernel)
+    int cluster = 2;                            // CTAs per cluster for the single-CTA residual-block kernel (ADB_TC_CLUSTER)
+    // Residual-block kernel of the bf16 sampling path, fixed when the handle is created (ADB_BLOCK_KERNEL):
+    //   3 (default) z-stash kernel + skip GEMM (wavenet_tc3.cuh)   2 pair kernel with the fp16 skip stash (wavenet_tc2.cuh)
+    //   1 pair kernel, fp32 skip read-modify-write in every block   0 single-CTA kernel (wavenet_tc.cuh)
+    // The training forward and the per-block debug entry point always use the pair kernel (they need every block's skip sum).
+    int block_kernel = 3;
+    int pair = 1;                               // derived: block_kernel != 0
+    int no_stash = 0;                           // derived: block_kernel == 1
+    int chunk = 256;                            // samples per pass of the bf16 stack (ADB_CHUNK): bounds the workspace
+    int64_t stash_budget = 80LL << 30;          // bytes the z stash may take (ADB_STASH_GB); fewer layers per skip GEMM if it does not fit
+    int dbg = 0;                                // ADB_DEBUG builds: ADB_DEBUG_FLAGS at create (2 = in-kernel cycle accounting)
+    float* skip_bias = nullptr;                 // [256] sum over layers of the skip half of b2
+    const float** d_b2 = nullptr;               // per-layer b2 pointers (device)
     std::vector<HMap> hmaps;
     bool tc_ready = false;
     // timing
@@ -548,6 +560,7 @@ static int refold(adb_wavenet* n) {
             CK(conv_cl_f32(a, 0));
         }
         pack_tc_tail_kernel<<<64, 256>>>(n->wsp_f, n->wsp_tc);
+        skip_bias_sum_kernel<<<1, 256>>>(n->d_b2, layers, n->skip_bias);
         cl_pack_conv_tc_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wsp_f, n->wsp_p, C, C, 1);
         cl_pack_conv_tc_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wspT, n->wspT_p, C, C, 1);
         CK(cudaGetLastError());
@@ -662,6 +675,13 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     CKN(dmalloc(n, &n->d_bp, layers));
     CKN(cudaMemcpy(n->d_wp, h_wp.data(), sizeof(float*) * layers, cudaMemcpyHostToDevice));
     CKN(cudaMemcpy(n->d_bp, h_bp.data(), sizeof(float*) * layers, cudaMemcpyHostToDevice));
+    {
+        std::vector<const float*> h_b2(layers);
+        for (int l = 0; l < layers; ++l) h_b2[l] = n->L[l].b2;
+        CKN(dmalloc(n, &n->d_b2, layers));
+        CKN(cudaMemcpy(n->d_b2, h_b2.data(), sizeof(float*) * layers, cudaMemcpyHostToDevice));
+        CKN(dmalloc(n, &n->skip_bias, 256));
+    }
     if (C == TC_C) {
         CKN(dmalloc(n, &n->wtc, static_cast<size_t>(layers) * 32 * 256 * 64));
         CKN(dmalloc(n, &n->wsp_tc, 4ULL * 256 * 64));
@@ -694,13 +714,26 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             const char* e = getenv("ADB_TC_CLUSTER");
             if (e) n->cluster = atoi(e);
             if (n->cluster != 1 && n->cluster != 2 && n->cluster != 4) n->cluster = 2;
-            const char* pe = getenv("ADB_TC_PAIR");
-            if (pe) n->pair = atoi(pe) != 0;
+            const char* be = getenv("ADB_BLOCK_KERNEL");
+            if (be) n->block_kernel = atoi(be);
+            if (n->block_kernel < 0 || n->block_kernel > 3) n->block_kernel = 3;
+            n->pair = n->block_kernel != 0;
+            n->no_stash = n->block_kernel == 1;
+            const char* ce = getenv("ADB_CHUNK");
+            if (ce && atoi(ce) > 0) n->chunk = atoi(ce);
+            const char* se = getenv("ADB_STASH_GB");
+            if (se && atof(se) > 0) n->stash_budget = static_cast<int64_t>(atof(se) * (1LL << 30));
+#ifdef ADB_DEBUG
+            const char* de = getenv("ADB_DEBUG_FLAGS");
+            if (de) n->dbg = atoi(de);
+#endif
         }
         if (rc2) { adb_wavenet_destroy(n); return rc2; }
         CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_skip_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_GEMM_SMEM_BYTES));
     }
     rc = refold(n);
     if (rc) { adb_wavenet_destroy(n); return rc; }
@@ -734,14 +767,28 @@ struct Workspace {
     float *xhat, *dslope, *fbuf, *xnext;  // sampler state, [B][L] each
     // fp32 path
     float *proj, *hA, *hB, *y, *z, *o, *skip, *s2;
-    // bf16 path
-    float* E;                            // [B][layers*1536]
+    // bf16 path: the residual stack runs over the batch in passes of Bc samples, so these are sized by Bc
+    float* E;                            // [Bc][layers*1536]
     __nv_bfloat16 *hbA, *hbB;
-    __nv_bfloat16* stash;             // [B][L][C] fp16 bits: an even layer's skip term, consumed by the next layer (pair kernel)
+    // z-stash kernel: [G][Bc][L][C] fp16 bits, the gated activations of G consecutive blocks (skip GEMM operand);
+    // pair kernel: [Bc][L][C] fp16 bits, an even block's skip term consumed by the next block
+    __nv_bfloat16* stash;
+    int Bc, G;
     int64_t total;
 };
 
-static Workspace carve(const adb_wavenet* n, int B, int L, int precision, void* base) {
+// layers per skip GEMM: all of them if the stash fits the budget, otherwise the largest count that does
+static int zs_group_layers(const adb_wavenet* n, int Bc, int L) {
+    const int64_t per_layer = static_cast<int64_t>(Bc) * L * n->C * 2;
+    int64_t g = n->stash_budget / per_layer;
+    if (g < 1) g = 1;
+    if (g > n->layers) g = n->layers;
+    return static_cast<int>(g);
+}
+
+// `whole_batch`: the training step and the per-block debug entry point run the stack over all B samples at once with the
+// pair kernel (they need every block's fp32 skip sum / saved inputs); sampling runs passes of at most n->chunk samples.
+static Workspace carve(const adb_wavenet* n, int B, int L, int precision, void* base, bool whole_batch = false) {
     Workspace w;
     memset(&w, 0, sizeof w);
     uint8_t* p = reinterpret_cast<uint8_t*>(base);
@@ -759,8 +806,9 @@ static Workspace carve(const adb_wavenet* n, int B, int L, int precision, void* 
     w.dslope = reinterpret_cast<float*>(take(BL * 4));
     w.fbuf = reinterpret_cast<float*>(take(BL * 4));
     w.xnext = reinterpret_cast<float*>(take(BL * 4));
-    w.skip = reinterpret_cast<float*>(take(BL * C * 4));
     if (precision == ADB_PRECISION_FP32) {
+        w.Bc = B; w.G = 1;
+        w.skip = reinterpret_cast<float*>(take(BL * C * 4));
         w.proj = reinterpret_cast<float*>(take(static_cast<int64_t>(n->layers) * B * C * 4));
         w.hA = reinterpret_cast<float*>(take(BL * C * 4));
         w.hB = reinterpret_cast<float*>(take(BL * C * 4));
@@ -769,10 +817,15 @@ static Workspace carve(const adb_wavenet* n, int B, int L, int precision, void* 
         w.o = reinterpret_cast<float*>(take(BL * 2 * C * 4));
         w.s2 = reinterpret_cast<float*>(take(BL * C * 4));
     } else {
-        w.E = reinterpret_cast<float*>(take(static_cast<int64_t>(B) * n->layers * 1536 * 4));
-        w.hbA = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
-        w.hbB = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
-        w.stash = reinterpret_cast<__nv_bfloat16*>(take(BL * C * 2));
+        w.Bc = (whole_batch || B < n->chunk) ? B : n->chunk;
+        const bool zs = !whole_batch && n->block_kernel == 3;
+        w.G = zs ? zs_group_layers(n, w.Bc, L) : 1;
+        const int64_t BcL = static_cast<int64_t>(w.Bc) * L;
+        w.skip = reinterpret_cast<float*>(take(BcL * C * 4));
+        w.E = reinterpret_cast<float*>(take(static_cast<int64_t>(w.Bc) * n->layers * 1536 * 4));
+        w.hbA = reinterpret_cast<__nv_bfloat16*>(take(BcL * C * 2));
+        w.hbB = reinterpret_cast<__nv_bfloat16*>(take(BcL * C * 2));
+        w.stash = reinterpret_cast<__nv_bfloat16*>(take(BcL * C * 2 * w.G));
     }
     w.total = off;
     return w;
@@ -818,6 +871,99 @@ static int check_forward_args(adb_wavenet* n, int B, int L, int precision, void*
     REQUIRE(ws && ws_bytes >= need, "workspace too small: %lld < %lld bytes", static_cast<long long>(ws_bytes),
             static_cast<long long>(need));
     REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+    return ADB_OK;
+}
+
+static int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// bf16 sampling path with the z-stash kernel (wavenet_tc3.cuh): the batch is processed in passes of w.Bc samples; every
+// block leaves its gated activations in the stash and one skip GEMM per w.G blocks contracts them into the fp32 skip sum.
+// `emb` ([B][512], embed_mlp_kernel) is already in w.emb.
+static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale, int in_scale_stride, float* out, int B, int L,
+                           const Workspace& w, cudaStream_t st) {
+    const int C = n->C, layers = n->layers;
+    const int num_sms = sm_count();
+    const int tiles_per_b = (L + TC_TILE_T - 1) / TC_TILE_T;
+    for (int b0 = 0; b0 < B; b0 += w.Bc) {
+        const int bc = (B - b0 < w.Bc) ? B - b0 : w.Bc;
+        const long long BL = static_cast<long long>(bc) * L;
+        {
+            ScopedTimer t(n, ADB_TIMER_AUX, st, 2);
+            ConvF32Args a;
+            memset(&a, 0, sizeof a);
+            a.in = w.emb + static_cast<long long>(b0) * 512; a.w = n->mtab; a.bias = n->cvec; a.out = w.E;
+            a.nb = 1; a.L = bc; a.Cin = 512; a.Cout = layers * 1536; a.taps = 1; a.dil = 1;
+            a.ldw = static_cast<long long>(layers) * 1536; a.ldo = a.ldw; a.in_scale = 1.f;
+            CK(conv_cl_f32(a, st));
+            in_proj_kernel<true><<<grid_for(BL * (C / 8)), 256, 0, st>>>(
+                x + static_cast<long long>(b0) * L, in_scale ? in_scale + static_cast<long long>(b0) * in_scale_stride : nullptr,
+                in_scale_stride, n->w_in_f, n->b_in, w.hbA, bc, L, C);
+            CK(cudaGetLastError());
+        }
+        const int num_tiles = tiles_per_b * bc;
+        int pairs = (num_tiles + 1) / 2;
+        if (pairs > num_sms / 2) pairs = num_sms / 2;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(TC_THREADS); lc.stream = st;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeClusterDimension;
+        la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+        lc.attrs = la; lc.numAttrs = 1;
+        CUtensorMap m_zst, m_zld, m_skip;
+        int rc = get_act_map(n, w.stash, w.G * bc, L, 1, &m_zst);
+        if (!rc) rc = get_act_map(n, w.stash, w.G * bc, L, 0, &m_zld);
+        if (!rc) rc = get_act_map(n, w.skip, bc, L, 2, &m_skip);
+        if (rc) return rc;
+        __nv_bfloat16 *hin = w.hbA, *hout = w.hbB;
+        for (int l = 0; l < layers; ++l) {
+            const int slot = l % w.G;
+            {
+                ScopedTimer t(n, ADB_TIMER_CONV, st);
+                CUtensorMap m_h, m_hout;
+                rc = get_act_map(n, hin, bc, L, 0, &m_h);
+                if (!rc) rc = get_act_map(n, hout, bc, L, 1, &m_hout);
+                if (rc) return rc;
+                BlockZsParams bp;
+                bp.E = w.E; bp.b2 = n->L[l].b2; bp.h_in = hin; bp.h_out_dbg = hout;
+                bp.B = bc; bp.L = L; bp.layer = l; bp.layers = layers; bp.dil = 1 << (l % n->cycle);
+                bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
+                bp.write_h = (l + 1 < layers) ? 1 : 0;
+                bp.zrow0 = slot * bc;
+                bp.dbg = n->dbg;
+                lc.dynamicSmemBytes = TC3_SMEM_BYTES;
+                CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel, m_h, n->tm_w2, m_hout, m_zst, bp));
+            }
+            { __nv_bfloat16* tmp = hin; hin = hout; hout = tmp; }
+            if (slot == w.G - 1 || l + 1 == layers) {
+                ScopedTimer t(n, ADB_TIMER_SKIP, st);
+                SkipGemmParams sp;
+                sp.G = slot + 1; sp.layer0 = l - slot;
+                sp.accumulate = sp.layer0 > 0 ? 1 : 0;
+                sp.bias = sp.accumulate ? nullptr : n->skip_bias;
+                sp.B = bc; sp.L = L; sp.tiles_per_b = tiles_per_b; sp.num_tiles = num_tiles;
+                lc.dynamicSmemBytes = SKIP_GEMM_SMEM_BYTES;
+                CK(cudaLaunchKernelEx(&lc, wavenet_skip_gemm_kernel, m_zld, n->tm_w2, m_skip, sp));
+            }
+        }
+        {
+            ScopedTimer t(n, ADB_TIMER_TAIL, st);
+            TailTcParams tp;
+            tp.skip = w.skip; tp.b_sp = n->b_sp; tp.w_out = n->w_out; tp.b_out = n->b_out;
+            tp.out = out + static_cast<long long>(b0) * L;
+            tp.scale = static_cast<float>(sqrt(1.0 / layers));
+            tp.B = bc; tp.L = L; tp.tiles_per_b = tiles_per_b; tp.num_tiles = num_tiles;
+            wavenet_tail_tc_kernel<<<num_tiles < num_sms ? num_tiles : num_sms, 256, TC_TAIL_SMEM_BYTES, st>>>(n->tm_wsp, tp);
+            CK(cudaGetLastError());
+        }
+    }
     return ADB_OK;
 }
 
@@ -879,6 +1025,9 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     }
 
     // ---------------- bf16 tensor-core path ----------------
+    if (!h_save && dump_layers == 0 && n->block_kernel == 3)
+        return forward_bf16_zs(n, x, in_scale, in_scale_stride, out, B, L, w, st);
+    REQUIRE(w.Bc == B, "internal: the pair-kernel path needs a whole-batch workspace (B=%d, pass=%d)", B, w.Bc);
     {
         ScopedTimer t(n, ADB_TIMER_AUX, st, 2);
         ConvF32Args a;
@@ -892,19 +1041,14 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
                                                                      B, L, C);
         CK(cudaGetLastError());
     }
-    int num_sms = 148;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int num_sms = sm_count();
     const int tiles_per_b = (L + TC_TILE_T - 1) / TC_TILE_T;
     const int num_tiles = tiles_per_b * B;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-    // residual-block kernel: persistent clusters of `cl` CTAs (weights multicast inside a cluster)
+    // single-CTA kernel: persistent clusters of `cl` CTAs (weights multicast inside a cluster)
     const int cl = n->cluster;
     int max_clusters = num_sms / cl;
-    if (cl > 1) {
+    if (cl > 1 && !n->pair) {
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3(num_sms / cl * cl); qc.blockDim = dim3(TC_THREADS); qc.dynamicSmemBytes = TC_BLOCK_SMEM_BYTES;
         cudaLaunchAttribute qa[1];
@@ -918,8 +1062,8 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     const int grid_block = (groups < max_clusters ? groups : max_clusters) * cl;
     __nv_bfloat16 *hin = h_save ? h_save : w.hbA, *hout = (h_save && layers > 1) ? h_save + BL * C : w.hbB;
     // pair kernel: even layers stash their skip term as fp16, odd layers add it and touch the fp32 sum once for both
-    // (off when per-layer skip sums are dumped for the debug entry point, or with ADB_NO_STASH=1)
-    const bool use_stash = n->pair && dump_layers == 0 && getenv("ADB_NO_STASH") == nullptr;
+    // (off when per-layer skip sums are dumped for the debug entry point, or with ADB_BLOCK_KERNEL=1)
+    const bool use_stash = n->pair && dump_layers == 0 && !n->no_stash;
     bool skip_written = false;
     for (int l = 0; l < layers; ++l) {
         ScopedTimer t(n, ADB_TIMER_CONV, st);
@@ -936,7 +1080,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
         bp.add_stash = (use_stash && (l & 1)) ? 1 : 0;
         if (use_stash && !(l & 1) && l + 1 < layers) bp.skip_mode = 2;
         else { bp.skip_mode = skip_written ? 0 : 1; skip_written = true; }
-        { const char* e = getenv("ADB_DEBUG_FLAGS"); bp.dbg = e ? atoi(e) : 0; }
+        bp.dbg = n->dbg;
         bp.cluster = cl;
         if (n->pair) {
             int pairs = (num_tiles + 1) / 2;
@@ -991,7 +1135,9 @@ extern "C" int adb_wavenet_forward_debug(adb_wavenet* n, const float* x, const f
     REQUIRE(x && c_noise && out, "null tensor argument");
     REQUIRE(dump_layers >= 0 && dump_layers <= n->layers, "bad dump_layers");
     REQUIRE(dump_layers == 0 || (dump_h && dump_skip), "dump buffers missing");
-    const Workspace w = carve(n, B, L, precision, ws);
+    const Workspace w = carve(n, B, L, precision, ws, dump_layers > 0);
+    REQUIRE(ws_bytes >= w.total, "workspace too small for the per-block dump: %lld < %lld bytes",
+            static_cast<long long>(ws_bytes), static_cast<long long>(w.total));
     return forward_impl(n, x, c_noise, in_scale, in_scale_stride, out, B, L, precision, w, dump_h, dump_skip, dump_layers,
                         S(stream));
 }

@@ -73,7 +73,7 @@ struct BlockTcParams {
     int tiles_per_b, num_tiles;
     int first_layer;                // 1: skip = value, 0: skip += value
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
-    int dbg;                        // debug bits (ADB_DEBUG_FLAGS): 1 = skip epilogue-2 global memory traffic
+    int dbg;                        // ADB_DEBUG builds only (ADB_DEBUG_FLAGS): 2 = in-kernel cycle accounting, other bits = timing experiments
     int cluster;                    // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across the cluster
     // pair kernel only — the fp32 skip sum is read-modify-written every SECOND layer:
     int skip_mode;                  // 0: skip += value (TMA reduce-add)  1: skip = value  2: stash the value as bf16 for the next layer
@@ -86,8 +86,14 @@ struct BlockTcParams {
 //  6 producer: total                            7 epi(warp 2): wait accumulator full (G1)    8 epi: epilogue-1 work
 //  9 epi: wait accumulator full (G2)           10 epi: epilogue-2 work                       11 epi: total
 __device__ unsigned long long g_tc_cycles[16];
-#define TC_DBG_T0(var) long long var = 0; if (p.dbg & 2) var = clock64()
-#define TC_DBG_ACC(idx, var) if (p.dbg & 2) dbg_acc[idx] += clock64() - var
+// Debug switches exist in -DADB_DEBUG builds only (libadb200_dbg.so, tools/): the release kernels carry no run-time predicate.
+#ifdef ADB_DEBUG
+#define TC_DBG_FLAGS(p) const int kdbg = (p).dbg
+#else
+#define TC_DBG_FLAGS(p) constexpr int kdbg = 0
+#endif
+#define TC_DBG_T0(var) long long var = 0; if (kdbg & 2) var = clock64()
+#define TC_DBG_ACC(idx, var) if (kdbg & 2) dbg_acc[idx] += clock64() - var
 
 enum TcWaitSite : uint32_t {
     SITE_PROD_EMPTY = 1, SITE_MMA_TEMPTY = 2, SITE_MMA_ZREADY = 3, SITE_MMA_FULL = 4, SITE_EPI_TFULL = 5,
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_hout, const __grid_constant__ CUtensorMap tm_skip,
                         const BlockTcParams p) {
+    TC_DBG_FLAGS(p);
     extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
     float* s_evec = reinterpret_cast<float*>(smem + BlockTcSmem::evec);
     float* s_b2 = reinterpret_cast<float*>(smem + BlockTcSmem::b2);
@@ -213,7 +220,7 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             }
         }
         TC_DBG_ACC(6, tp_all);
-        if ((p.dbg & 2) && lane == 0) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
+        if ((kdbg & 2) && lane == 0) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         uint32_t stage = 0, phase = 0;
@@ -280,7 +287,7 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             }
         }
         TC_DBG_ACC(4, tm_all);
-        if ((p.dbg & 2) && lane == 0)
+        if ((kdbg & 2) && lane == 0)
             for (int i = 0; i < 5; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
     } else {
         // ===================== epilogue warps =====================
@@ -396,7 +403,7 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 TC_DBG_T0(tk3);
                 ++use0;
                 tc_fence_after_sync();
-                const bool st_ok = tile_valid && (t < p.L) && !(p.dbg & 1);
+                const bool st_ok = tile_valid && (t < p.L) && !(kdbg & 1);
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     const int col = half * 128 + cc * 32;     // residual channel of r[0]
@@ -456,7 +463,7 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && tile_valid && !(p.dbg & 1)) {
+                    if (lane == 0 && tile_valid && !(kdbg & 1)) {
                         if (p.first_layer) tma_store_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
                         else               tma_reduce_add_3d(&tm_skip, stg + (cc & 1) * 4096, col, trow, b);
                         tma_store_commit();
@@ -473,7 +480,7 @@ wavenet_block_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             TC_DBG_ACC(10, tk2);
         }
         TC_DBG_ACC(11, te_all);
-        if ((p.dbg & 2) && warp == 2 && lane == 0)
+        if ((kdbg & 2) && warp == 2 && lane == 0)
             for (int i = 7; i < 12; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores fully performed before exit
     }

@@ -48,6 +48,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                           const __grid_constant__ CUtensorMap tm_skip, const __grid_constant__ CUtensorMap tm_hout,
                           const __grid_constant__ CUtensorMap tm_stash_ld, const __grid_constant__ CUtensorMap tm_stash_st,
                           const BlockTcParams p) {
+    TC_DBG_FLAGS(p);
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_evec = reinterpret_cast<float*>(smem + Tc2Smem::evec);
     float* s_esum = reinterpret_cast<float*>(smem + Tc2Smem::esum);
@@ -131,7 +132,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
             const int tile = grp * 2 + rank;
             const int b = tile / p.tiles_per_b;           // >= B for a padding tile: TMA zero-fills
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
-            if ((p.dbg & 4) && lane < 4 && grp + num_pairs < num_groups) {
+            if ((kdbg & 4) && lane < 4 && grp + num_pairs < num_groups) {
                 // warm L2 with the centre-tap rows of this CTA's NEXT tile (first touch of those rows: the dilated
                 // taps re-read rows that neighbouring tiles of the same wave already pulled in)
                 const int ntile = (grp + num_pairs) * 2 + rank;
@@ -169,7 +170,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
             }
         }
         TC_DBG_ACC(6, tp_all);
-        if ((p.dbg & 2) && lane == 0 && leader) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
+        if ((kdbg & 2) && lane == 0 && leader) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
     } else if (warp == 1) {
         if (leader) {
             // ===================== MMA issuer (rank 0 only) =====================
@@ -240,7 +241,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                 }
             }
             TC_DBG_ACC(4, tm_all);
-            if ((p.dbg & 2) && lane == 0)
+            if ((kdbg & 2) && lane == 0)
                 for (int i = 0; i < 5; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
         }
     } else {
@@ -366,7 +367,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                         const float v1 = (__uint_as_float(r[i + 1]) + s_b2[col + i + 1]) * 0.70710678118654752f;
                         pk[i >> 1] = pack_bf16x2(v0, v1);
                     }
-                    if (!(p.dbg & 64)) {
+                    if (!(kdbg & 64)) {
                         // the 32 x 32-channel chunk leaves as ONE asynchronous TMA tensor store from this warp's 2 KB buffer
                         // (rows of 64 bytes, 64-byte swizzle); rows past L are clipped by the hardware
                         if (lane == 0) tma_store_wait_read<0>();       // previous chunk's store has read the buffer
@@ -377,7 +378,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                                 make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0 && tile_valid && !(p.dbg & 17)) {
+                        if (lane == 0 && tile_valid && !(kdbg & 17)) {
                             tma_store_3d(&tm_hout, tbuf, col, t0 + q * 32, b);
                             tma_store_commit();
                         }
@@ -395,7 +396,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                         const int c = lane & 3;                    // 16-byte chunk of the 64-byte row segment
                         const uint4 v = *reinterpret_cast<const uint4*>(tbuf + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4));
                         const int tt = t0 + q * 32 + rr;
-                        if (tile_valid && tt < p.L && !(p.dbg & 17))
+                        if (tile_valid && tt < p.L && !(kdbg & 17))
                             *reinterpret_cast<uint4*>(p.h_out + (static_cast<long long>(b) * p.L + tt) * TC_C + col + c * 8) = v;
                     }
                 }
@@ -437,7 +438,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                                 make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0 && tile_valid && !(p.dbg & 33)) {
+                        if (lane == 0 && tile_valid && !(kdbg & 33)) {
                             tma_store_3d(&tm_stash_st, cbuf, col, trow, b);
                             tma_store_commit();
                         }
@@ -456,7 +457,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && tile_valid && !(p.dbg & 33)) {
+                    if (lane == 0 && tile_valid && !(kdbg & 33)) {
                         if (p.skip_mode == 1) tma_store_3d(&tm_skip, cbuf, col, trow, b);
                         else                  tma_reduce_add_3d(&tm_skip, cbuf, col, trow, b);
                         tma_store_commit();
@@ -473,7 +474,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
             TC_DBG_ACC(10, tk2);
         }
         TC_DBG_ACC(11, te_all);
-        if ((p.dbg & 2) && warp == 2 && lane == 0 && leader)
+        if ((kdbg & 2) && warp == 2 && lane == 0 && leader)
             for (int i = 7; i < 12; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }

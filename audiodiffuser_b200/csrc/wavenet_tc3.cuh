@@ -1,0 +1,619 @@
+// Residual-block kernel, third generation ("z-stash"), and the skip GEMM that goes with it.
+//
+// wavenet.py:94-115 per block:  y = DilatedConv(h + p) ; z = sigmoid(y_gate) * tanh(y_filter) ; o = W2 z + b2 ;
+//                               h' = (h + o[:C]) / sqrt(2) ; skip_l = o[C:]
+// wavenet.py:145-151:           skip = sum_l skip_l ; tail(skip / sqrt(layers))
+//
+// The sum over blocks of the skip halves is ONE contraction with K = layers x 256:
+//     skip[t][n] = sum_l sum_k z_l[t][k] W2s_l[n][k] + sum_l b2s_l[n]
+// so the block kernel does not compute its skip half at all. It only leaves its gated activations z_l (fp16, 2 bytes per
+// element, already sitting in shared memory as GEMM2's A operand in exactly the layout a TMA tensor store wants) in a
+// per-layer stash, and `wavenet_skip_gemm_kernel` contracts the whole stash against the stacked skip weights afterwards
+// with the accumulator resident in TMEM across all layers: the fp32 skip sum is written once per evaluation instead of
+// being read-modify-written by every (second) block. Relative to the pair kernel of wavenet_tc2.cuh a block launch loses
+//   * the skip GEMM job (1/8 of its MMA work, 128 KB of weight loads and 64 KB of stash loads per tile),
+//   * epilogue 2s (128 KB of TMEM reads, 128 KB of staging writes, the fp32 TMA reduce-adds at L2),
+//   * the identity MMAs and the 64 KB activation re-load that added the residual input: the epilogue reads its own 64
+//     bytes of h per chunk straight from global memory (L2 hits: the tile was just loaded as the centre tap),
+// which is what the shared-memory port (MMA operand reads + TMA writes + epilogue LSU traffic share 128 B/clk) and the
+// L2 write path were saturated with. Everything else (CTA pair, cta_group::2 M = 256 MMAs, 4 x 32 KB stages, exact
+// step-embedding fold, fp16 GEMM2) is the design of wavenet_tc2.cuh.
+//
+// TMEM: 2 accumulators x 256 columns; the jobs of a tile group (G1a, G1b, G2r) simply alternate between them, so the
+// accumulator a job uses is (running job counter & 1).
+#pragma once
+#include "wavenet_tc.cuh"
+
+namespace adb {
+
+constexpr int T3_STAGES = 4;
+constexpr int T3_A_BYTES = 128 * 64 * 2;            // 16 KB: this CTA's [128 t][64 ci] activation block
+constexpr int T3_B_BYTES = 128 * 64 * 2;            // 16 KB: this CTA's half [128 n][64 k] of a weight tile
+constexpr int T3_STAGE_BYTES = T3_A_BYTES + T3_B_BYTES;
+
+struct Tc3Smem {
+    static constexpr int stages = 0;
+    static constexpr int z = T3_STAGES * T3_STAGE_BYTES;            // 64 KB gated activations (GEMM2 A operand, stash source, h' staging)
+    static constexpr int evec = z + TC_Z_BYTES;                     // 3 x 512 fp32
+    static constexpr int esum = evec + 3 * 512 * 4;                 // 512 fp32
+    static constexpr int b2 = esum + 512 * 4;                       // 256 fp32 (residual half of the output bias)
+    static constexpr int bars = b2 + 256 * 4;
+    static constexpr int tmem_ptr = bars + 16 * 8;
+    static constexpr int total = tmem_ptr + 16;
+};
+static_assert(Tc3Smem::z % 1024 == 0, "swizzle alignment");
+static_assert(Tc3Smem::total <= 232448, "shared memory budget");
+constexpr int TC3_SMEM_BYTES = Tc3Smem::total;
+
+struct BlockZsParams {
+    const float* E;                 // [B][layers][3][512] epilogue-1 constants for this evaluation
+    const float* b2;                // [512] output-projection bias of this layer (first 256 used here)
+    const __nv_bfloat16* h_in;      // [B][L][256] (residual input, read by epilogue 2)
+    __nv_bfloat16* h_out_dbg;       // ADB_DEBUG builds only: h' for the LSU-store timing experiment
+    int B, L, layer, layers, dil;
+    int tiles_per_b, num_tiles;
+    int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
+    int zrow0;                      // first "batch" coordinate of this layer's slot in the stash map (slot * B)
+    int dbg;                        // ADB_DEBUG builds only: 2 = in-kernel cycle accounting; timing experiments (results wrong):
+                                    // 4 no A re-load for G1b, 8 no stash stores, 16 no h' stores, 32 no gate math, 64 no residual read,
+                                    // 256 h' through LSU stores instead of TMA, 1024 all stores to a fixed L2-resident tile per CTA
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
+                        const __grid_constant__ CUtensorMap tm_hout, const __grid_constant__ CUtensorMap tm_zst,
+                        const BlockZsParams p) {
+    TC_DBG_FLAGS(p);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_evec = reinterpret_cast<float*>(smem + Tc3Smem::evec);
+    float* s_esum = reinterpret_cast<float*>(smem + Tc3Smem::esum);
+    float* s_b2 = reinterpret_cast<float*>(smem + Tc3Smem::b2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Tc3Smem::bars);
+    uint64_t* bar_full = bars;                   // [T3_STAGES] (rank 0's copy is the live one)
+    uint64_t* bar_empty = bars + T3_STAGES;      // [T3_STAGES] per CTA
+    uint64_t* bar_tfull = bars + 2 * T3_STAGES;  // [2] per CTA
+    uint64_t* bar_tempty = bar_tfull + 2;        // [2] rank 0
+    uint64_t* bar_zready = bar_tempty + 2;       // [2] rank 0
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Tc3Smem::tmem_ptr);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_h);
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_hout);
+        tma_prefetch_desc(&tm_zst);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < T3_STAGES; ++s) { mbar_init(&bar_full[s], 2); mbar_init(&bar_empty[s], 1); }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_tfull[i], 1);
+                mbar_init(&bar_tempty[i], 2 * (TC_EPI_THREADS / 32));
+                mbar_init(&bar_zready[i], 2 * (TC_EPI_THREADS / 32));
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair(s_tmem, 512);
+        tmem_relinquish_pair();
+    }
+    if (warp >= 2)
+        for (int i = threadIdx.x - 64; i < 256; i += TC_EPI_THREADS) s_b2[i] = p.b2[i];
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+    constexpr uint32_t IDESC = umma_idesc_pair_bf16(256);
+    constexpr uint32_t IDESC_F16 = umma_idesc_pair_f16(256);
+
+    const int pair_id = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_groups = (p.num_tiles + 1) >> 1;
+    const int njobs = p.write_h ? 3 : 2;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        uint32_t stage = 0, phase = 0;
+        long long dbg_acc[12] = {};
+        TC_DBG_T0(tp_all);
+        for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
+            const int tile = grp * 2 + rank;
+            const int b = tile / p.tiles_per_b;           // >= B for a padding tile: TMA zero-fills
+            const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
+            for (int job = 0; job < njobs; ++job) {
+                const int nkb = job < 2 ? 12 : 4;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    TC_DBG_T0(tw);
+                    mbar_wait(&bar_empty[stage], phase ^ 1, SITE_PROD_EMPTY, stage);
+                    TC_DBG_ACC(5, tw);
+                    if (lane == 0) {
+                        uint8_t* sa = smem + Tc3Smem::stages + stage * T3_STAGE_BYTES;
+                        uint8_t* sb = sa + T3_A_BYTES;
+                        const int wblk = p.layer * TC_W_BLOCKS_PER_LAYER + (job < 2 ? job * 12 + kb : 24 + kb);
+                        const bool load_a = job < 2 && !((kdbg & 4) && job == 1);     // timing experiment: G1b re-uses stale A tiles
+                        const uint32_t bytes = load_a ? T3_STAGE_BYTES : T3_B_BYTES;
+                        if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * bytes);   // both CTAs' bytes
+                        else        mbar_arrive_cluster(&bar_full[stage], 0);
+                        if (load_a) {
+                            const int tap = kb >> 2, cib = kb & 3;
+                            tma_load_3d_pair(sa, &tm_h, &bar_full[stage], cib * 64, t0 + (tap - 1) * p.dil, b);
+                        }
+                        tma_load_2d_pair(sb, &tm_w, &bar_full[stage], 0, wblk * 256 + rank * 128);
+                    }
+                    __syncwarp();
+                    if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        TC_DBG_ACC(6, tp_all);
+        if ((kdbg & 2) && lane == 0 && leader) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===================== MMA issuer (rank 0 only) =====================
+            uint32_t stage = 0, phase = 0;
+            uint32_t jg = 0;                      // jobs issued so far: accumulator = jg & 1, its use count = jg >> 1
+            uint32_t it = 0;
+            const uint32_t z_addr = smem_u32(smem + Tc3Smem::z);
+            long long dbg_acc[12] = {};
+            TC_DBG_T0(tm_all);
+            for (int grp = pair_id; grp < num_groups; grp += num_pairs, ++it) {
+                for (int job = 0; job < njobs; ++job, ++jg) {
+                    const uint32_t buf = jg & 1;
+                    TC_DBG_T0(tw0);
+                    mbar_wait(&bar_tempty[buf], ((jg >> 1) & 1) ^ 1, SITE_MMA_TEMPTY, job);
+                    TC_DBG_ACC(job < 2 ? 0 : 1, tw0);
+                    if (job == 2) {
+                        // z K-blocks 0,1 come from epilogue 1a, K-blocks 2,3 from epilogue 1b: start on the first half
+                        // while 1b is still running (the second wait sits inside the K loop)
+                        TC_DBG_T0(tw1);
+                        mbar_wait(&bar_zready[0], it & 1, SITE_MMA_ZREADY, 0);
+                        TC_DBG_ACC(2, tw1);
+                    }
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + buf * 256;
+                    const int nkb = job < 2 ? 12 : 4;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (job == 2 && kb == 2) {
+                            TC_DBG_T0(tw1);
+                            mbar_wait(&bar_zready[1], it & 1, SITE_MMA_ZREADY, 1);
+                            TC_DBG_ACC(2, tw1);
+                            tc_fence_after_sync();
+                        }
+                        TC_DBG_T0(tw2);
+                        mbar_wait(&bar_full[stage], phase, SITE_MMA_FULL, stage);
+                        TC_DBG_ACC(3, tw2);
+                        tc_fence_after_sync();
+                        if (lane == 0) {
+                            const uint32_t sa = smem_u32(smem + Tc3Smem::stages + stage * T3_STAGE_BYTES);
+                            const uint32_t a_addr = job < 2 ? sa : z_addr + kb * TC_A_BYTES;
+                            const uint32_t b_addr = sa + T3_A_BYTES;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_ss_pair(d_tmem, umma_desc_sw128_kmajor(a_addr + k * 32),
+                                                  umma_desc_sw128_kmajor(b_addr + k * 32), job < 2 ? IDESC : IDESC_F16,
+                                                  (kb | k) != 0 ? 1u : 0u);
+                            umma_commit_pair_mc(&bar_empty[stage], 3);           // stage free in both CTAs
+                            if (kb == nkb - 1) umma_commit_pair_mc(&bar_tfull[buf], 3);   // accumulator ready in both CTAs
+                        }
+                        __syncwarp();
+                        if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+            TC_DBG_ACC(4, tm_all);
+            if ((kdbg & 2) && lane == 0)
+                for (int i = 0; i < 5; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs) =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int half = ew >> 2;             // which half of the columns this warp handles
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* zbase = smem + Tc3Smem::z;
+        // the two 4 KB pieces of the z buffer this warp owns: rows 32 q .. 32 q + 31 of K-blocks (half) and (2 + half).
+        // It writes its z values there, hands them to TMA (stash store), and later stages its h' chunks in the same bytes.
+        uint8_t* own0 = zbase + half * TC_A_BYTES + q * 4096;
+        uint8_t* own1 = zbase + (2 + half) * TC_A_BYTES + q * 4096;
+        uint32_t jg = 0;
+        long long dbg_acc[12] = {};
+        TC_DBG_T0(te_all);
+        const float* Ec = s_evec + 512;
+        const float* E0 = s_evec;
+        const float* E2 = s_evec + 1024;
+        for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
+            const int tile = grp * 2 + rank;
+            const bool tile_valid = tile < p.num_tiles;
+            const int b = tile / p.tiles_per_b;
+            const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
+            const int t = t0 + row;
+            named_bar_sync(1, TC_EPI_THREADS);
+            {
+                const float* src = p.E + (static_cast<long long>(tile_valid ? b : 0) * p.layers + p.layer) * 1536;
+                for (int i = threadIdx.x - 64; i < 1536; i += TC_EPI_THREADS) s_evec[i] = src[i];
+            }
+            named_bar_sync(1, TC_EPI_THREADS);
+            for (int i = threadIdx.x - 64; i < 512; i += TC_EPI_THREADS)
+                s_esum[i] = (s_evec[i] + s_evec[512 + i] + s_evec[1024 + i]) * (i < 256 ? 0.5f : 1.0f);
+            named_bar_sync(1, TC_EPI_THREADS);
+            const float m_lo = (t >= p.dil) ? 1.0f : 0.0f;
+            const float m_hi = (t < p.L - p.dil) ? 1.0f : 0.0f;
+            const bool interior = (t0 >= p.dil) && (t0 + TC_TILE_T - 1 < p.L - p.dil);
+
+            // ---- epilogue 1: gate; z -> shared memory (GEMM2 A operand) and -> the stash (TMA store) ----
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j, ++jg) {
+                const uint32_t buf = jg & 1;
+                TC_DBG_T0(tw);
+                mbar_wait(&bar_tfull[buf], (jg >> 1) & 1, SITE_EPI_TFULL, j);
+                TC_DBG_ACC(7, tw);
+                TC_DBG_T0(tk);
+                tc_fence_after_sync();
+                if (j == 0) {
+                    // the previous tile's h' stores were staged in the bytes this tile's z goes to
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
+                uint8_t* own = j ? own1 : own0;
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int col = half * 64 + cc * 32;
+                    uint32_t g[32], f[32];
+                    tmem_ld_32x32(t_lane + buf * 256 + col, g);
+                    tmem_ld_32x32(t_lane + buf * 256 + 128 + col, f);
+                    tmem_ld_wait();
+                    const int c0 = 128 * j + col;
+                    uint32_t packed[16];
+                    if (kdbg & 32) {                               // timing experiment: no gate math
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) packed[i >> 1] = pack_f16x2(__uint_as_float(g[i]), __uint_as_float(f[i + 1]));
+                    } else if (interior) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float g0 = fmaf(__uint_as_float(g[i]), 0.5f, s_esum[c0 + i]);
+                            const float g1 = fmaf(__uint_as_float(g[i + 1]), 0.5f, s_esum[c0 + i + 1]);
+                            const float f0 = __uint_as_float(f[i]) + s_esum[256 + c0 + i];
+                            const float f1 = __uint_as_float(f[i + 1]) + s_esum[256 + c0 + i + 1];
+                            const uint32_t tg = tanh_f16x2(pack_f16x2(g0, g1));
+                            const uint32_t tf = tanh_f16x2(pack_f16x2(f0, f1));
+                            packed[i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float gv[2], fv[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int c = c0 + i + u;
+                                gv[u] = __uint_as_float(g[i + u]) + Ec[c];
+                                fv[u] = __uint_as_float(f[i + u]) + Ec[256 + c];
+                                gv[u] = fmaf(m_lo, E0[c], gv[u]);
+                                fv[u] = fmaf(m_lo, E0[256 + c], fv[u]);
+                                gv[u] = 0.5f * fmaf(m_hi, E2[c], gv[u]);
+                                fv[u] = fmaf(m_hi, E2[256 + c], fv[u]);
+                            }
+                            const uint32_t tg = tanh_f16x2(pack_f16x2(gv[0], gv[1]));
+                            const uint32_t tf = tanh_f16x2(pack_f16x2(fv[0], fv[1]));
+                            packed[i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
+                        }
+                    }
+                    uint8_t* zrow = own + lane * 128;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int chunk = (4 * cc + m) ^ (lane & 7);
+                        *reinterpret_cast<uint4*>(zrow + chunk * 16) =
+                            make_uint4(packed[4 * m], packed[4 * m + 1], packed[4 * m + 2], packed[4 * m + 3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_cluster(&bar_tempty[buf], 0);
+                    mbar_arrive_cluster(&bar_zready[j], 0);
+                    // this warp's [32 t][64 ch] piece of z_l leaves for the stash (128-byte rows, one 4 KB box)
+                    if (tile_valid && !(kdbg & 8)) {
+                        // 1024 (timing experiment): every CTA stores to its own fixed tile, so the stores never leave L2
+                        const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : t0;
+                        const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : b;
+                        tma_store_3d(&tm_zst, own, (2 * j + half) * 64, st0 + q * 32, p.zrow0 + sb);
+                        tma_store_commit();
+                    }
+                }
+                __syncwarp();
+                TC_DBG_ACC(8, tk);
+            }
+
+            // ---- epilogue 2: h' = (h + W2r z + b) / sqrt(2) -> bf16, staged as two [32 t][64 ch] boxes in this warp's own
+            //      pieces of the z buffer (idle once GEMM2 has completed) and stored by TMA.
+            if (p.write_h) {
+                // residual input: this thread's row, 128 channels, fetched before the accumulator wait
+                uint32_t hres[4][16];
+                {
+                    const bool ok = tile_valid && t < p.L && !(kdbg & 64);     // 64: timing experiment without the residual read
+                    const __nv_bfloat16* hrow = p.h_in + (static_cast<long long>(ok ? b : 0) * p.L + (ok ? t : 0)) * TC_C + half * 128;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        if (ok) {
+                            uint32_t lo[8], hi[8];
+                            ldg256(hrow + cc * 32, lo);
+                            ldg256(hrow + cc * 32 + 16, hi);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { hres[cc][i] = lo[i]; hres[cc][8 + i] = hi[i]; }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) hres[cc][i] = 0u;
+                        }
+                    }
+                }
+                const uint32_t buf = jg & 1;
+                TC_DBG_T0(tw3);
+                mbar_wait(&bar_tfull[buf], (jg >> 1) & 1, SITE_EPI_TFULL, 2);
+                TC_DBG_ACC(9, tw3);
+                TC_DBG_T0(tk3);
+                ++jg;
+                tc_fence_after_sync();
+                if (lane == 0) tma_store_wait_read<0>();       // the stash stores have read this warp's pieces of z
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int col = half * 128 + cc * 32;
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_lane + buf * 256 + col, r);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const uint32_t hv = hres[cc][i >> 1];
+                        const float v0 = (__uint_as_float(r[i]) + bf16_lo(hv) + s_b2[col + i]) * 0.70710678118654752f;
+                        const float v1 = (__uint_as_float(r[i + 1]) + bf16_hi(hv) + s_b2[col + i + 1]) * 0.70710678118654752f;
+                        pk[i >> 1] = pack_bf16x2(v0, v1);
+                    }
+                    if ((kdbg & 256) && tile_valid && t < p.L) {   // timing experiment: h' leaves through the LSU, two full sectors per thread
+                        __nv_bfloat16* dst = p.h_out_dbg + (static_cast<long long>(b) * p.L + t) * TC_C + col;
+                        uint32_t lo[8], hi[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
+                        stg256(dst, lo);
+                        stg256(dst + 16, hi);
+                    }
+                    uint8_t* own = (cc & 2) ? own1 : own0;
+                    uint8_t* srow = own + lane * 128;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int chunk = (4 * (cc & 1) + m) ^ (lane & 7);
+                        *reinterpret_cast<uint4*>(srow + chunk * 16) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+                    }
+                    if (cc & 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && tile_valid && !(kdbg & (16 | 256))) {
+                            const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : t0;
+                            const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : b;
+                            tma_store_3d(&tm_hout, own, half * 128 + (cc >> 1) * 64, st0 + q * 32, sb);
+                            tma_store_commit();
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&bar_tempty[buf], 0);
+                TC_DBG_ACC(10, tk3);
+            }
+        }
+        TC_DBG_ACC(11, te_all);
+        if ((kdbg & 2) && warp == 2 && lane == 0 && leader)
+            for (int i = 7; i < 12; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores fully performed before exit
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skip GEMM: skip[b][t][n] (=|+=) bias[n] + sum_{l < G} sum_k z_l[b][t][k] W2s_{layer0 + l}[n][k]
+// (wavenet.py:114 skip half summed over blocks, :145-149). Persistent CTA pairs, one M = 256 x N = 256 fp16 MMA stream
+// per tile group with K = 256 G, two TMEM accumulators so a group's epilogue overlaps the next group's MMAs, 5 x 32 KB
+// stages. The epilogue leaves fp32 [32 t][32 ch] boxes through TMA (plain store for the first layer group, reduce-add
+// for later ones).
+// ------------------------------------------------------------------------------------------------
+constexpr int SG_STAGES = 5;
+struct SkipGemmSmem {
+    static constexpr int stages = 0;
+    static constexpr int stg = SG_STAGES * T3_STAGE_BYTES;          // 8 warps x 2 x 4 KB fp32 transposition boxes
+    static constexpr int bias = stg + 8 * 8192;                     // 256 fp32
+    static constexpr int bars = bias + 1024;
+    static constexpr int tmem_ptr = bars + 16 * 8;
+    static constexpr int total = tmem_ptr + 16;
+};
+static_assert(SkipGemmSmem::stg % 1024 == 0, "swizzle alignment");
+static_assert(SkipGemmSmem::total <= 232448, "shared memory budget");
+constexpr int SKIP_GEMM_SMEM_BYTES = SkipGemmSmem::total;
+
+struct SkipGemmParams {
+    const float* bias;              // [256] sum over ALL layers of the skip half of b2, or nullptr (later layer groups)
+    int B, L, tiles_per_b, num_tiles;
+    int G;                          // layers in this group (stash slots 0 .. G-1)
+    int layer0;                     // first layer of the group (weight blocks)
+    int accumulate;                 // 0: skip = value   1: skip += value (TMA reduce-add)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wavenet_skip_gemm_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w,
+                         const __grid_constant__ CUtensorMap tm_skip, const SkipGemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_bias = reinterpret_cast<float*>(smem + SkipGemmSmem::bias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SkipGemmSmem::bars);
+    uint64_t* bar_full = bars;                   // [SG_STAGES] rank 0
+    uint64_t* bar_empty = bars + SG_STAGES;      // [SG_STAGES] per CTA
+    uint64_t* bar_tfull = bars + 2 * SG_STAGES;  // [2] per CTA
+    uint64_t* bar_tempty = bar_tfull + 2;        // [2] rank 0
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SkipGemmSmem::tmem_ptr);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_z);
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_skip);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < SG_STAGES; ++s) { mbar_init(&bar_full[s], 2); mbar_init(&bar_empty[s], 1); }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_tfull[i], 1);
+                mbar_init(&bar_tempty[i], 2 * (TC_EPI_THREADS / 32));
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair(s_tmem, 512);
+        tmem_relinquish_pair();
+    }
+    if (warp >= 2)
+        for (int i = threadIdx.x - 64; i < 256; i += TC_EPI_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+    constexpr uint32_t IDESC_F16 = umma_idesc_pair_f16(256);
+
+    const int pair_id = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_groups = (p.num_tiles + 1) >> 1;
+    const int nkb = 4 * p.G;
+
+    if (warp == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
+            const int tile = grp * 2 + rank;
+            const bool tile_valid = tile < p.num_tiles;
+            const int b = tile_valid ? tile / p.tiles_per_b : 0;     // a padding tile re-reads sample 0 (never stored)
+            const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&bar_empty[stage], phase ^ 1, SITE_PROD_EMPTY, stage);
+                if (lane == 0) {
+                    uint8_t* sa = smem + SkipGemmSmem::stages + stage * T3_STAGE_BYTES;
+                    uint8_t* sb = sa + T3_A_BYTES;
+                    const int l = kb >> 2, cib = kb & 3;
+                    const int wblk = (p.layer0 + l) * TC_W_BLOCKS_PER_LAYER + 28 + cib;
+                    if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * T3_STAGE_BYTES);
+                    else        mbar_arrive_cluster(&bar_full[stage], 0);
+                    tma_load_3d_pair(sa, &tm_z, &bar_full[stage], cib * 64, t0, l * p.B + b);
+                    tma_load_2d_pair(sb, &tm_w, &bar_full[stage], 0, wblk * 256 + rank * 128);
+                }
+                __syncwarp();
+                if (++stage == SG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int grp = pair_id; grp < num_groups; grp += num_pairs, ++it) {
+                const uint32_t buf = it & 1;
+                mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1, SITE_MMA_TEMPTY, 0);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bar_full[stage], phase, SITE_MMA_FULL, stage);
+                    tc_fence_after_sync();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + SkipGemmSmem::stages + stage * T3_STAGE_BYTES);
+                        const uint32_t sb = sa + T3_A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss_pair(d_tmem, umma_desc_sw128_kmajor(sa + k * 32), umma_desc_sw128_kmajor(sb + k * 32),
+                                              IDESC_F16, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair_mc(&bar_empty[stage], 3);
+                        if (kb == nkb - 1) umma_commit_pair_mc(&bar_tfull[buf], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == SG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* stg = smem + SkipGemmSmem::stg + ew * 8192;
+        uint32_t it = 0;
+        for (int grp = pair_id; grp < num_groups; grp += num_pairs, ++it) {
+            const int tile = grp * 2 + rank;
+            const bool tile_valid = tile < p.num_tiles;
+            const int b = tile / p.tiles_per_b;
+            const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
+            const int trow = t0 + q * 32;
+            const uint32_t buf = it & 1;
+            mbar_wait(&bar_tfull[buf], (it >> 1) & 1, SITE_EPI_TFULL, 0);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col = half * 128 + cc * 32;
+                uint32_t r[32];
+                tmem_ld_32x32(t_lane + buf * 256 + col, r);
+                tmem_ld_wait();
+                uint8_t* cbuf = stg + (cc & 1) * 4096;
+                if (lane == 0) tma_store_wait_read<1>();      // box (cc & 1) was handed to TMA two commits ago
+                __syncwarp();
+                uint8_t* brow = cbuf + lane * 128;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    float4 v;
+                    v.x = __uint_as_float(r[4 * m + 0]) + s_bias[col + 4 * m + 0];
+                    v.y = __uint_as_float(r[4 * m + 1]) + s_bias[col + 4 * m + 1];
+                    v.z = __uint_as_float(r[4 * m + 2]) + s_bias[col + 4 * m + 2];
+                    v.w = __uint_as_float(r[4 * m + 3]) + s_bias[col + 4 * m + 3];
+                    const int chunk = m ^ (lane & 7);
+                    *reinterpret_cast<float4*>(brow + chunk * 16) = v;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && tile_valid) {
+                    if (p.accumulate) tma_reduce_add_3d(&tm_skip, cbuf, col, trow, b);
+                    else              tma_store_3d(&tm_skip, cbuf, col, trow, b);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bar_tempty[buf], 0);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// bias[n] = sum_l b2_l[256 + n]  (the skip half of every block's output-projection bias, wavenet.py:114)
+__global__ void skip_bias_sum_kernel(const float* const* __restrict__ b2_tab, int layers, float* __restrict__ out) {
+    const int n = threadIdx.x;
+    float s = 0.f;
+    for (int l = 0; l < layers; ++l) s += b2_tab[l][256 + n];
+    out[n] = s;
+}
+
+}  // namespace adb

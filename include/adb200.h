@@ -165,7 +165,8 @@ int adb_wavenet_sample_edm(adb_wavenet* net, const float* noise_dev, const float
 #define ADB_TIMER_STEP 1   /* fused sampler-step kernels */
 #define ADB_TIMER_AUX 2    /* embedding MLP / E table / input projection */
 #define ADB_TIMER_TAIL 3   /* skip-projection + output-projection kernel(s) */
-#define ADB_TIMER_COUNT 4
+#define ADB_TIMER_SKIP 4   /* skip GEMM over the stashed gated activations (z-stash path) */
+#define ADB_TIMER_COUNT 5
 /* Enable (1) / disable (0) event timing around kernel classes inside adb_wavenet_sample_edm and
  * adb_wavenet_forward; adb_wavenet_timers() synchronises and returns accumulated ms and kernel-launch counts per class
  * (launch counts are maintained whether or not timing is enabled). */
