@@ -367,6 +367,7 @@ struct adb_wavenet {
     //   1 pair kernel, fp32 skip read-modify-write in every block   0 single-CTA kernel (wavenet_tc.cuh)
     // The training forward and the per-block debug entry point always use the pair kernel (they need every block's skip sum).
     int block_kernel = 3;
+    int zs_pipe = 1;                            // z-stash kernel: software-pipelined job order (ADB_ZS_PIPE=0: plain per-group order)
     int pair = 1;                               // derived: block_kernel != 0
     int no_stash = 0;                           // derived: block_kernel == 1
     int chunk = 256;                            // samples per pass of the bf16 stack (ADB_CHUNK): bounds the workspace
@@ -719,6 +720,8 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             if (n->block_kernel < 0 || n->block_kernel > 3) n->block_kernel = 3;
             n->pair = n->block_kernel != 0;
             n->no_stash = n->block_kernel == 1;
+            const char* pe = getenv("ADB_ZS_PIPE");
+            if (pe) n->zs_pipe = atoi(pe) != 0;
             const char* ce = getenv("ADB_CHUNK");
             if (ce && atoi(ce) > 0) n->chunk = atoi(ce);
             const char* se = getenv("ADB_STASH_GB");
@@ -732,7 +735,8 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
-        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_skip_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_GEMM_SMEM_BYTES));
     }
     rc = refold(n);
@@ -929,7 +933,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 ScopedTimer t(n, ADB_TIMER_CONV, st);
                 CUtensorMap m_h, m_hout;
                 rc = get_act_map(n, hin, bc, L, 0, &m_h);
-                if (!rc) rc = get_act_map(n, hout, bc, L, 1, &m_hout);
+                if (!rc) rc = get_act_map(n, hout, bc, L, 4, &m_hout);
                 if (rc) return rc;
                 BlockZsParams bp;
                 bp.E = w.E; bp.b2 = n->L[l].b2; bp.h_in = hin; bp.h_out_dbg = hout;
@@ -939,7 +943,8 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 bp.zrow0 = slot * bc;
                 bp.dbg = n->dbg;
                 lc.dynamicSmemBytes = TC3_SMEM_BYTES;
-                CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel, m_h, n->tm_w2, m_hout, m_zst, bp));
+                if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true>, m_h, n->tm_w2, m_hout, m_zst, bp));
+                else            CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false>, m_h, n->tm_w2, m_hout, m_zst, bp));
             }
             { __nv_bfloat16* tmp = hin; hin = hout; hout = tmp; }
             if (slot == w.G - 1 || l + 1 == layers) {

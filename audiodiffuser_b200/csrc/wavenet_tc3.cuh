@@ -30,18 +30,18 @@ constexpr int T3_STAGES = 4;
 constexpr int T3_A_BYTES = 128 * 64 * 2;            // 16 KB: this CTA's [128 t][64 ci] activation block
 constexpr int T3_B_BYTES = 128 * 64 * 2;            // 16 KB: this CTA's half [128 n][64 k] of a weight tile
 constexpr int T3_STAGE_BYTES = T3_A_BYTES + T3_B_BYTES;
+constexpr int T3_STG_BYTES = 4096;                  // per epilogue warp: two [32 t][32 ch] bf16 boxes (64-byte rows) for h'
 
 struct Tc3Smem {
     static constexpr int stages = 0;
-    static constexpr int z = T3_STAGES * T3_STAGE_BYTES;            // 64 KB gated activations (GEMM2 A operand, stash source, h' staging)
-    static constexpr int evec = z + TC_Z_BYTES;                     // 3 x 512 fp32
-    static constexpr int esum = evec + 3 * 512 * 4;                 // 512 fp32
-    static constexpr int b2 = esum + 512 * 4;                       // 256 fp32 (residual half of the output bias)
-    static constexpr int bars = b2 + 256 * 4;
+    static constexpr int z = T3_STAGES * T3_STAGE_BYTES;            // 64 KB gated activations (GEMM2 A operand, stash source)
+    static constexpr int stg = z + TC_Z_BYTES;                      // 8 x 4 KB h' staging
+    static constexpr int esum = stg + 8 * T3_STG_BYTES;             // 512 fp32
+    static constexpr int bars = esum + 512 * 4;
     static constexpr int tmem_ptr = bars + 16 * 8;
     static constexpr int total = tmem_ptr + 16;
 };
-static_assert(Tc3Smem::z % 1024 == 0, "swizzle alignment");
+static_assert(Tc3Smem::z % 1024 == 0 && Tc3Smem::stg % 1024 == 0, "swizzle alignment");
 static_assert(Tc3Smem::total <= 232448, "shared memory budget");
 constexpr int TC3_SMEM_BYTES = Tc3Smem::total;
 
@@ -56,18 +56,40 @@ struct BlockZsParams {
     int zrow0;                      // first "batch" coordinate of this layer's slot in the stash map (slot * B)
     int dbg;                        // ADB_DEBUG builds only: 2 = in-kernel cycle accounting; timing experiments (results wrong):
                                     // 4 no A re-load for G1b, 8 no stash stores, 16 no h' stores, 32 no gate math, 64 no residual read,
-                                    // 256 h' through LSU stores instead of TMA, 1024 all stores to a fixed L2-resident tile per CTA
+                                    // 1024 all stores to a fixed L2-resident tile per CTA
 };
 
+// Job order of one CTA pair over its n tile groups. Types: 0 = G1a (gate / filter of channels 0..127), 1 = G1b (128..255),
+// 2 = G2r (residual projection). PIPE = false: G1a(i) G1b(i) G2r(i) per group. PIPE = true (software-pipelined):
+//     G1a(0) G1b(0) | G1a(1) G2r(0) G1b(1) | G1a(2) G2r(1) G1b(2) | ... | G2r(n-1)
+// G2r(i) needs the gated activations of BOTH halves, i.e. epilogue 1b of G1b(i), which takes ~2 k cycles after G1b(i)
+// completes; issuing the next group's G1a in between gives the tensor pipe 6 k cycles of independent work instead of a
+// bubble. The producer, the MMA issuer and the epilogue warps all walk this sequence; slot s of the pipelined order that
+// has no job (i + 1 == n) returns false.
+template <bool PIPE>
+__device__ __forceinline__ int zs_num_slots(int n, int write_h) {
+    if (!write_h) return 2 * n;
+    return PIPE ? 2 + 3 * n : 3 * n;
+}
+template <bool PIPE>
+__device__ __forceinline__ bool zs_job_at(int s, int n, int write_h, int& type, int& i) {
+    if (!write_h) { i = s >> 1; type = s & 1; return true; }
+    if (!PIPE) { i = s / 3; type = s - 3 * i; return true; }
+    if (s < 2) { i = 0; type = s; return true; }
+    const int u = s - 2, g = u / 3, r = u - 3 * g;
+    if (r == 1) { i = g; type = 2; return true; }
+    i = g + 1; type = r == 0 ? 0 : 1;
+    return i < n;
+}
+
+template <bool PIPE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_hout, const __grid_constant__ CUtensorMap tm_zst,
                         const BlockZsParams p) {
     TC_DBG_FLAGS(p);
     extern __shared__ __align__(1024) uint8_t smem[];
-    float* s_evec = reinterpret_cast<float*>(smem + Tc3Smem::evec);
     float* s_esum = reinterpret_cast<float*>(smem + Tc3Smem::esum);
-    float* s_b2 = reinterpret_cast<float*>(smem + Tc3Smem::b2);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Tc3Smem::bars);
     uint64_t* bar_full = bars;                   // [T3_STAGES] (rank 0's copy is the live one)
     uint64_t* bar_empty = bars + T3_STAGES;      // [T3_STAGES] per CTA
@@ -101,8 +123,6 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         tmem_alloc_pair(s_tmem, 512);
         tmem_relinquish_pair();
     }
-    if (warp >= 2)
-        for (int i = threadIdx.x - 64; i < 256; i += TC_EPI_THREADS) s_b2[i] = p.b2[i];
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();
@@ -114,40 +134,41 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     const int pair_id = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
     const int num_groups = (p.num_tiles + 1) >> 1;
-    const int njobs = p.write_h ? 3 : 2;
+    const int n_mine = (num_groups - pair_id + num_pairs - 1) / num_pairs;     // tile groups of this CTA pair (>= 1)
+    const int n_slots = zs_num_slots<PIPE>(n_mine, p.write_h);
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
         uint32_t stage = 0, phase = 0;
         long long dbg_acc[12] = {};
         TC_DBG_T0(tp_all);
-        for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
-            const int tile = grp * 2 + rank;
+        for (int s = 0; s < n_slots; ++s) {
+            int job, gi;
+            if (!zs_job_at<PIPE>(s, n_mine, p.write_h, job, gi)) continue;
+            const int tile = (pair_id + gi * num_pairs) * 2 + rank;
             const int b = tile / p.tiles_per_b;           // >= B for a padding tile: TMA zero-fills
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
-            for (int job = 0; job < njobs; ++job) {
-                const int nkb = job < 2 ? 12 : 4;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    TC_DBG_T0(tw);
-                    mbar_wait(&bar_empty[stage], phase ^ 1, SITE_PROD_EMPTY, stage);
-                    TC_DBG_ACC(5, tw);
-                    if (lane == 0) {
-                        uint8_t* sa = smem + Tc3Smem::stages + stage * T3_STAGE_BYTES;
-                        uint8_t* sb = sa + T3_A_BYTES;
-                        const int wblk = p.layer * TC_W_BLOCKS_PER_LAYER + (job < 2 ? job * 12 + kb : 24 + kb);
-                        const bool load_a = job < 2 && !((kdbg & 4) && job == 1);     // timing experiment: G1b re-uses stale A tiles
-                        const uint32_t bytes = load_a ? T3_STAGE_BYTES : T3_B_BYTES;
-                        if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * bytes);   // both CTAs' bytes
-                        else        mbar_arrive_cluster(&bar_full[stage], 0);
-                        if (load_a) {
-                            const int tap = kb >> 2, cib = kb & 3;
-                            tma_load_3d_pair(sa, &tm_h, &bar_full[stage], cib * 64, t0 + (tap - 1) * p.dil, b);
-                        }
-                        tma_load_2d_pair(sb, &tm_w, &bar_full[stage], 0, wblk * 256 + rank * 128);
+            const int nkb = job < 2 ? 12 : 4;
+            for (int kb = 0; kb < nkb; ++kb) {
+                TC_DBG_T0(tw);
+                mbar_wait(&bar_empty[stage], phase ^ 1, SITE_PROD_EMPTY, stage);
+                TC_DBG_ACC(5, tw);
+                if (lane == 0) {
+                    uint8_t* sa = smem + Tc3Smem::stages + stage * T3_STAGE_BYTES;
+                    uint8_t* sb = sa + T3_A_BYTES;
+                    const int wblk = p.layer * TC_W_BLOCKS_PER_LAYER + (job < 2 ? job * 12 + kb : 24 + kb);
+                    const bool load_a = job < 2 && !((kdbg & 4) && job == 1);     // timing experiment: G1b re-uses stale A tiles
+                    const uint32_t bytes = load_a ? T3_STAGE_BYTES : T3_B_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * bytes);   // both CTAs' bytes
+                    else        mbar_arrive_cluster(&bar_full[stage], 0);
+                    if (load_a) {
+                        const int tap = kb >> 2, cib = kb & 3;
+                        tma_load_3d_pair(sa, &tm_h, &bar_full[stage], cib * 64, t0 + (tap - 1) * p.dil, b);
                     }
-                    __syncwarp();
-                    if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+                    tma_load_2d_pair(sb, &tm_w, &bar_full[stage], 0, wblk * 256 + rank * 128);
                 }
+                __syncwarp();
+                if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
             }
         }
         TC_DBG_ACC(6, tp_all);
@@ -157,53 +178,52 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             // ===================== MMA issuer (rank 0 only) =====================
             uint32_t stage = 0, phase = 0;
             uint32_t jg = 0;                      // jobs issued so far: accumulator = jg & 1, its use count = jg >> 1
-            uint32_t it = 0;
             const uint32_t z_addr = smem_u32(smem + Tc3Smem::z);
             long long dbg_acc[12] = {};
             TC_DBG_T0(tm_all);
-            for (int grp = pair_id; grp < num_groups; grp += num_pairs, ++it) {
-                for (int job = 0; job < njobs; ++job, ++jg) {
-                    const uint32_t buf = jg & 1;
-                    TC_DBG_T0(tw0);
-                    mbar_wait(&bar_tempty[buf], ((jg >> 1) & 1) ^ 1, SITE_MMA_TEMPTY, job);
-                    TC_DBG_ACC(job < 2 ? 0 : 1, tw0);
-                    if (job == 2) {
-                        // z K-blocks 0,1 come from epilogue 1a, K-blocks 2,3 from epilogue 1b: start on the first half
-                        // while 1b is still running (the second wait sits inside the K loop)
-                        TC_DBG_T0(tw1);
-                        mbar_wait(&bar_zready[0], it & 1, SITE_MMA_ZREADY, 0);
-                        TC_DBG_ACC(2, tw1);
-                    }
-                    tc_fence_after_sync();
-                    const uint32_t d_tmem = tmem_base + buf * 256;
-                    const int nkb = job < 2 ? 12 : 4;
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        if (job == 2 && kb == 2) {
-                            TC_DBG_T0(tw1);
-                            mbar_wait(&bar_zready[1], it & 1, SITE_MMA_ZREADY, 1);
-                            TC_DBG_ACC(2, tw1);
-                            tc_fence_after_sync();
-                        }
-                        TC_DBG_T0(tw2);
-                        mbar_wait(&bar_full[stage], phase, SITE_MMA_FULL, stage);
-                        TC_DBG_ACC(3, tw2);
-                        tc_fence_after_sync();
-                        if (lane == 0) {
-                            const uint32_t sa = smem_u32(smem + Tc3Smem::stages + stage * T3_STAGE_BYTES);
-                            const uint32_t a_addr = job < 2 ? sa : z_addr + kb * TC_A_BYTES;
-                            const uint32_t b_addr = sa + T3_A_BYTES;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16_ss_pair(d_tmem, umma_desc_sw128_kmajor(a_addr + k * 32),
-                                                  umma_desc_sw128_kmajor(b_addr + k * 32), job < 2 ? IDESC : IDESC_F16,
-                                                  (kb | k) != 0 ? 1u : 0u);
-                            umma_commit_pair_mc(&bar_empty[stage], 3);           // stage free in both CTAs
-                            if (kb == nkb - 1) umma_commit_pair_mc(&bar_tfull[buf], 3);   // accumulator ready in both CTAs
-                        }
-                        __syncwarp();
-                        if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
-                    }
+            for (int s = 0; s < n_slots; ++s) {
+                int job, gi;
+                if (!zs_job_at<PIPE>(s, n_mine, p.write_h, job, gi)) continue;
+                const uint32_t buf = jg & 1;
+                TC_DBG_T0(tw0);
+                mbar_wait(&bar_tempty[buf], ((jg >> 1) & 1) ^ 1, SITE_MMA_TEMPTY, job);
+                TC_DBG_ACC(job < 2 ? 0 : 1, tw0);
+                if (job == 2) {
+                    // z K-blocks 0,1 come from epilogue 1a, K-blocks 2,3 from epilogue 1b (second wait inside the K loop)
+                    TC_DBG_T0(tw1);
+                    mbar_wait(&bar_zready[0], gi & 1, SITE_MMA_ZREADY, 0);
+                    TC_DBG_ACC(2, tw1);
                 }
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                const int nkb = job < 2 ? 12 : 4;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (job == 2 && kb == 2) {
+                        TC_DBG_T0(tw1);
+                        mbar_wait(&bar_zready[1], gi & 1, SITE_MMA_ZREADY, 1);
+                        TC_DBG_ACC(2, tw1);
+                        tc_fence_after_sync();
+                    }
+                    TC_DBG_T0(tw2);
+                    mbar_wait(&bar_full[stage], phase, SITE_MMA_FULL, stage);
+                    TC_DBG_ACC(3, tw2);
+                    tc_fence_after_sync();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + Tc3Smem::stages + stage * T3_STAGE_BYTES);
+                        const uint32_t a_addr = job < 2 ? sa : z_addr + kb * TC_A_BYTES;
+                        const uint32_t b_addr = sa + T3_A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss_pair(d_tmem, umma_desc_sw128_kmajor(a_addr + k * 32),
+                                              umma_desc_sw128_kmajor(b_addr + k * 32), job < 2 ? IDESC : IDESC_F16,
+                                              (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair_mc(&bar_empty[stage], 3);           // stage free in both CTAs
+                        if (kb == nkb - 1) umma_commit_pair_mc(&bar_tfull[buf], 3);   // accumulator ready in both CTAs
+                    }
+                    __syncwarp();
+                    if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+                }
+                ++jg;
             }
             TC_DBG_ACC(4, tm_all);
             if ((kdbg & 2) && lane == 0)
@@ -218,50 +238,79 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         uint8_t* zbase = smem + Tc3Smem::z;
         // the two 4 KB pieces of the z buffer this warp owns: rows 32 q .. 32 q + 31 of K-blocks (half) and (2 + half).
-        // It writes its z values there, hands them to TMA (stash store), and later stages its h' chunks in the same bytes.
+        // It writes its z values there and hands the same bytes to TMA for the stash store.
         uint8_t* own0 = zbase + half * TC_A_BYTES + q * 4096;
         uint8_t* own1 = zbase + (2 + half) * TC_A_BYTES + q * 4096;
+        uint8_t* tbuf = smem + Tc3Smem::stg + ew * T3_STG_BYTES;
+        const float* b2g = p.b2 + half * 128;
         uint32_t jg = 0;
+        uint32_t zp[2][16];                   // gated activations of a G1a job whose z write waits for the previous G2r (PIPE)
+        bool z_pending = false;
+        int pend_t0 = 0, pend_b = 0;
+        bool pend_valid = false;
         long long dbg_acc[12] = {};
         TC_DBG_T0(te_all);
-        const float* Ec = s_evec + 512;
-        const float* E0 = s_evec;
-        const float* E2 = s_evec + 1024;
-        for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
-            const int tile = grp * 2 + rank;
+
+        // write this warp's 32 x 64-channel piece of z (from zp) into K-block 2 j + half, publish it to the MMA issuer and send it
+        // to the stash
+        auto publish_z = [&](int j, int zt0, int zb, bool zvalid) {
+            uint8_t* own = j ? own1 : own0;
+            if (lane == 0) tma_store_wait_read<0>();      // the previous stash store from these bytes has been read
+            __syncwarp();
+            uint8_t* zrow = own + lane * 128;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int chunk = (4 * cc + m) ^ (lane & 7);
+                    *reinterpret_cast<uint4*>(zrow + chunk * 16) = make_uint4(zp[cc][4 * m], zp[cc][4 * m + 1], zp[cc][4 * m + 2], zp[cc][4 * m + 3]);
+                }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cluster(&bar_zready[j], 0);
+                if (zvalid && !(kdbg & 8)) {
+                    // 1024 (timing experiment): every CTA stores to its own fixed tile, so the stores never leave L2
+                    const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : zt0;
+                    const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : zb;
+                    tma_store_3d(&tm_zst, own, (2 * j + half) * 64, st0 + q * 32, p.zrow0 + sb);
+                    tma_store_commit();
+                }
+            }
+            __syncwarp();
+        };
+
+        for (int s = 0; s < n_slots; ++s) {
+            int job, gi;
+            if (!zs_job_at<PIPE>(s, n_mine, p.write_h, job, gi)) continue;
+            const int tile = (pair_id + gi * num_pairs) * 2 + rank;
             const bool tile_valid = tile < p.num_tiles;
             const int b = tile / p.tiles_per_b;
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
             const int t = t0 + row;
-            named_bar_sync(1, TC_EPI_THREADS);
-            {
-                const float* src = p.E + (static_cast<long long>(tile_valid ? b : 0) * p.layers + p.layer) * 1536;
-                for (int i = threadIdx.x - 64; i < 1536; i += TC_EPI_THREADS) s_evec[i] = src[i];
-            }
-            named_bar_sync(1, TC_EPI_THREADS);
-            for (int i = threadIdx.x - 64; i < 512; i += TC_EPI_THREADS)
-                s_esum[i] = (s_evec[i] + s_evec[512 + i] + s_evec[1024 + i]) * (i < 256 ? 0.5f : 1.0f);
-            named_bar_sync(1, TC_EPI_THREADS);
-            const float m_lo = (t >= p.dil) ? 1.0f : 0.0f;
-            const float m_hi = (t < p.L - p.dil) ? 1.0f : 0.0f;
-            const bool interior = (t0 >= p.dil) && (t0 + TC_TILE_T - 1 < p.L - p.dil);
-
-            // ---- epilogue 1: gate; z -> shared memory (GEMM2 A operand) and -> the stash (TMA store) ----
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j, ++jg) {
-                const uint32_t buf = jg & 1;
+            const uint32_t buf = jg & 1;
+            const uint32_t par = (jg >> 1) & 1;
+            ++jg;
+            if (job < 2) {
+                // ---- epilogue 1: gate ----
+                const float* Eg = p.E + (static_cast<long long>(tile_valid ? b : 0) * p.layers + p.layer) * 1536;
+                if (job == 0) {
+                    // interior tiles (every row sees all three taps) add ONE vector: E0 + E1 + E2, gate half pre-scaled by 1/2
+                    named_bar_sync(1, TC_EPI_THREADS);            // everyone is done with the previous group's vector
+                    for (int i = threadIdx.x - 64; i < 512; i += TC_EPI_THREADS)
+                        s_esum[i] = (Eg[i] + Eg[512 + i] + Eg[1024 + i]) * (i < 256 ? 0.5f : 1.0f);
+                    named_bar_sync(1, TC_EPI_THREADS);
+                }
+                const float m_lo = (t >= p.dil) ? 1.0f : 0.0f;
+                const float m_hi = (t < p.L - p.dil) ? 1.0f : 0.0f;
+                const bool interior = (t0 >= p.dil) && (t0 + TC_TILE_T - 1 < p.L - p.dil);
+                const int j = job;
                 TC_DBG_T0(tw);
-                mbar_wait(&bar_tfull[buf], (jg >> 1) & 1, SITE_EPI_TFULL, j);
+                mbar_wait(&bar_tfull[buf], par, SITE_EPI_TFULL, j);
                 TC_DBG_ACC(7, tw);
                 TC_DBG_T0(tk);
                 tc_fence_after_sync();
-                if (j == 0) {
-                    // the previous tile's h' stores were staged in the bytes this tile's z goes to
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
-                }
-                uint8_t* own = j ? own1 : own0;
-#pragma unroll 1
+#pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const int col = half * 64 + cc * 32;
                     uint32_t g[32], f[32];
@@ -269,10 +318,9 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                     tmem_ld_32x32(t_lane + buf * 256 + 128 + col, f);
                     tmem_ld_wait();
                     const int c0 = 128 * j + col;
-                    uint32_t packed[16];
                     if (kdbg & 32) {                               // timing experiment: no gate math
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) packed[i >> 1] = pack_f16x2(__uint_as_float(g[i]), __uint_as_float(f[i + 1]));
+                        for (int i = 0; i < 32; i += 2) zp[cc][i >> 1] = pack_f16x2(__uint_as_float(g[i]), __uint_as_float(f[i + 1]));
                     } else if (interior) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
@@ -282,59 +330,49 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                             const float f1 = __uint_as_float(f[i + 1]) + s_esum[256 + c0 + i + 1];
                             const uint32_t tg = tanh_f16x2(pack_f16x2(g0, g1));
                             const uint32_t tf = tanh_f16x2(pack_f16x2(f0, f1));
-                            packed[i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
+                            zp[cc][i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
                         }
                     } else {
+                        // boundary tile (~4 % of the tiles): per-row tap masks, constants straight from global memory
+                        const float* Ec = Eg + 512;
+                        const float* E0 = Eg;
+                        const float* E2 = Eg + 1024;
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
                             float gv[2], fv[2];
 #pragma unroll
                             for (int u = 0; u < 2; ++u) {
                                 const int c = c0 + i + u;
-                                gv[u] = __uint_as_float(g[i + u]) + Ec[c];
-                                fv[u] = __uint_as_float(f[i + u]) + Ec[256 + c];
-                                gv[u] = fmaf(m_lo, E0[c], gv[u]);
-                                fv[u] = fmaf(m_lo, E0[256 + c], fv[u]);
-                                gv[u] = 0.5f * fmaf(m_hi, E2[c], gv[u]);
-                                fv[u] = fmaf(m_hi, E2[256 + c], fv[u]);
+                                gv[u] = __uint_as_float(g[i + u]) + __ldg(Ec + c);
+                                fv[u] = __uint_as_float(f[i + u]) + __ldg(Ec + 256 + c);
+                                gv[u] = fmaf(m_lo, __ldg(E0 + c), gv[u]);
+                                fv[u] = fmaf(m_lo, __ldg(E0 + 256 + c), fv[u]);
+                                gv[u] = 0.5f * fmaf(m_hi, __ldg(E2 + c), gv[u]);
+                                fv[u] = fmaf(m_hi, __ldg(E2 + 256 + c), fv[u]);
                             }
                             const uint32_t tg = tanh_f16x2(pack_f16x2(gv[0], gv[1]));
                             const uint32_t tf = tanh_f16x2(pack_f16x2(fv[0], fv[1]));
-                            packed[i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
+                            zp[cc][i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
                         }
                     }
-                    uint8_t* zrow = own + lane * 128;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const int chunk = (4 * cc + m) ^ (lane & 7);
-                        *reinterpret_cast<uint4*>(zrow + chunk * 16) =
-                            make_uint4(packed[4 * m], packed[4 * m + 1], packed[4 * m + 2], packed[4 * m + 3]);
-                    }
                 }
-                fence_proxy_async_smem();
+                // the accumulator is drained: hand it back before touching shared memory
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_cluster(&bar_tempty[buf], 0);
-                    mbar_arrive_cluster(&bar_zready[j], 0);
-                    // this warp's [32 t][64 ch] piece of z_l leaves for the stash (128-byte rows, one 4 KB box)
-                    if (tile_valid && !(kdbg & 8)) {
-                        // 1024 (timing experiment): every CTA stores to its own fixed tile, so the stores never leave L2
-                        const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : t0;
-                        const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : b;
-                        tma_store_3d(&tm_zst, own, (2 * j + half) * 64, st0 + q * 32, p.zrow0 + sb);
-                        tma_store_commit();
-                    }
+                if (lane == 0) mbar_arrive_cluster(&bar_tempty[buf], 0);
+                // K-blocks 0,1 of z are still being read by the PREVIOUS group's G2r when that job was issued after this G1a
+                // (pipelined order): keep the values in registers until its accumulator-ready event, which is next in line.
+                // G1b is always issued after the previous G2r, so its completion already implies that z is free.
+                if (PIPE && p.write_h && j == 0 && gi > 0) {
+                    z_pending = true; pend_t0 = t0; pend_b = b; pend_valid = tile_valid;
+                } else {
+                    publish_z(j, t0, b, tile_valid);
                 }
-                __syncwarp();
                 TC_DBG_ACC(8, tk);
-            }
-
-            // ---- epilogue 2: h' = (h + W2r z + b) / sqrt(2) -> bf16, staged as two [32 t][64 ch] boxes in this warp's own
-            //      pieces of the z buffer (idle once GEMM2 has completed) and stored by TMA.
-            if (p.write_h) {
-                // residual input: this thread's row, 128 channels, fetched before the accumulator wait
-                uint32_t hres[4][16];
+            } else {
+                // ---- epilogue 2: h' = (h + W2r z + b) / sqrt(2) -> bf16. Each 32 x 32-channel chunk is transposed through one of
+                //      this warp's two 2 KB boxes (64-byte rows, 64-byte swizzle) and leaves as an asynchronous TMA tensor store.
+                uint32_t hres[4][16];         // residual input: this thread's row, 128 channels, fetched before the accumulator wait
                 {
                     const bool ok = tile_valid && t < p.L && !(kdbg & 64);     // 64: timing experiment without the residual read
                     const __nv_bfloat16* hrow = p.h_in + (static_cast<long long>(ok ? b : 0) * p.L + (ok ? t : 0)) * TC_C + half * 128;
@@ -352,15 +390,16 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                         }
                     }
                 }
-                const uint32_t buf = jg & 1;
                 TC_DBG_T0(tw3);
-                mbar_wait(&bar_tfull[buf], (jg >> 1) & 1, SITE_EPI_TFULL, 2);
+                mbar_wait(&bar_tfull[buf], par, SITE_EPI_TFULL, 2);
                 TC_DBG_ACC(9, tw3);
                 TC_DBG_T0(tk3);
-                ++jg;
                 tc_fence_after_sync();
-                if (lane == 0) tma_store_wait_read<0>();       // the stash stores have read this warp's pieces of z
-                __syncwarp();
+                if (z_pending) {              // this G2r has finished reading z: the next group's K-blocks 0,1 can land
+                    publish_z(0, pend_t0, pend_b, pend_valid);
+                    z_pending = false;
+                }
+                const int sw_w = (lane >> 1) & 3;                 // write swizzle of this lane's own row
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const int col = half * 128 + cc * 32;
@@ -371,34 +410,23 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
                         const uint32_t hv = hres[cc][i >> 1];
-                        const float v0 = (__uint_as_float(r[i]) + bf16_lo(hv) + s_b2[col + i]) * 0.70710678118654752f;
-                        const float v1 = (__uint_as_float(r[i + 1]) + bf16_hi(hv) + s_b2[col + i + 1]) * 0.70710678118654752f;
+                        const float v0 = (__uint_as_float(r[i]) + bf16_lo(hv) + __ldg(b2g + cc * 32 + i)) * 0.70710678118654752f;
+                        const float v1 = (__uint_as_float(r[i + 1]) + bf16_hi(hv) + __ldg(b2g + cc * 32 + i + 1)) * 0.70710678118654752f;
                         pk[i >> 1] = pack_bf16x2(v0, v1);
                     }
-                    if ((kdbg & 256) && tile_valid && t < p.L) {   // timing experiment: h' leaves through the LSU, two full sectors per thread
-                        __nv_bfloat16* dst = p.h_out_dbg + (static_cast<long long>(b) * p.L + t) * TC_C + col;
-                        uint32_t lo[8], hi[8];
+                    uint8_t* box = tbuf + (cc & 1) * 2048;
+                    if (lane == 0) tma_store_wait_read<1>();       // the store that last used this box (two commits ago) has read it
+                    __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
-                        stg256(dst, lo);
-                        stg256(dst + 16, hi);
-                    }
-                    uint8_t* own = (cc & 2) ? own1 : own0;
-                    uint8_t* srow = own + lane * 128;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const int chunk = (4 * (cc & 1) + m) ^ (lane & 7);
-                        *reinterpret_cast<uint4*>(srow + chunk * 16) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
-                    }
-                    if (cc & 1) {
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0 && tile_valid && !(kdbg & (16 | 256))) {
-                            const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : t0;
-                            const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : b;
-                            tma_store_3d(&tm_hout, own, half * 128 + (cc >> 1) * 64, st0 + q * 32, sb);
-                            tma_store_commit();
-                        }
+                    for (int m = 0; m < 4; ++m)
+                        *reinterpret_cast<uint4*>(box + lane * 64 + ((m ^ sw_w) << 4)) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && tile_valid && !(kdbg & 16)) {
+                        const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : t0;
+                        const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : b;
+                        tma_store_3d(&tm_hout, box, col, st0 + q * 32, sb);
+                        tma_store_commit();
                     }
                 }
                 tc_fence_before_sync();

@@ -1,6 +1,6 @@
 """Import the reference's own modules (build container only; test infrastructure).
 
-`/root/reference` exists only in the build container. Two third-party imports of the reference
+`/root/reference` exists only in the build container (the GPU box gets `baseline/_ref`, see `_find_root`). Two third-party imports of the reference
 are absent from this image and are stubbed exactly as SURVEY.md §8(c) describes:
 `torchsde` (used only by Brownian-tree classes, components/utils.py:54-102) and
 `einops_exts.rearrange_many` (attention_utils.py:5).
@@ -9,7 +9,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ADB_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """`/root/reference` in the build container; on the GPU box the verbatim, git-ignored copy that baseline/install_ref.py
+    made of the modules on the hot path (`baseline/_ref`)."""
+    for cand in (os.environ.get("ADB_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "src", "models", "components")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():

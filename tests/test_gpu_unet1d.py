@@ -4,7 +4,7 @@ Tolerances (BASELINE.json north_star): fp32 path <= 1e-5 rel-L2 per call, bf16 p
 import pytest
 import torch
 
-from conftest import load_golden, rel_l2
+from conftest import record_parity, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-5, "bf16": 2e-2}
@@ -81,7 +81,9 @@ def test_unet_edm_denoiser_and_sampler(dev, precision):
     assert smp.last_nfe == 2 * steps - 1
     e = rel_l2(x, g["heun"])
     print(f"unet EDM heun {precision}: rel-L2 {e:.3e}")
-    assert e < (1e-4 if precision == "fp32" else 1e-1), (precision, e)
+    record_parity(f"unet1d_mid_edm_heun_{precision}", rel_l2_vs_reference=e, nfe=smp.last_nfe)
+    # measured 3.6e-7 (fp32) / 1.5e-3 (bf16): the gates leave a factor ~6, not 60
+    assert e < (5e-6 if precision == "fp32" else 1e-2), (precision, e)
 
 
 def test_unet_rejects_conditioning(dev):
