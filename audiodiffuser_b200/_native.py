@@ -6,7 +6,7 @@ current CUDA stream.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p, POINTER
 
 import torch
 
@@ -33,6 +33,7 @@ _SIGS = {
                                     c_int64, c_void_p]),
     "adb_edm_scale": (c_int, [c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "adb_edm_axpy": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
+    "adb_edm_churn_rng": (c_int, [c_void_p, c_void_p, c_float, c_float, c_uint64, c_int, c_int64, c_int, c_int64, c_void_p]),
     "adb_edm_euler": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "adb_edm_rk2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p,
                             c_int64, c_void_p]),
@@ -46,6 +47,9 @@ _SIGS = {
     "adb_edm_noise_in": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64,
                                  c_void_p]),
     "adb_edm_dsm_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int64, c_void_p]),
+    "adb_edm_dsm_loss_masked": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "adb_edm_dsm_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                      c_void_p]),
     "adb_wavenet_param_count": (c_int64, [c_int, c_int]),
     "adb_wavenet_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int64, c_int]),
     "adb_wavenet_load_params": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
@@ -60,6 +64,9 @@ _SIGS = {
     "adb_wavenet_sample_edm": (c_int, [c_void_p, c_void_p, _F, c_int, c_int, c_float, c_float, c_float, c_float,
                                        c_float, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_int64, POINTER(c_int), c_void_p]),
+    "adb_wavenet_sample_edm_seeded": (c_int, [c_void_p, c_void_p, _F, c_int, c_int, c_float, c_float, c_float, c_float,
+                                              c_float, c_int, c_float, c_void_p, c_uint64, c_int64, c_void_p, c_int, c_int, c_int,
+                                              c_void_p, c_int64, POINTER(c_int), c_void_p]),
     "adb_cl_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_cl_conv_packed_elems": (c_int64, [c_int, c_int, c_int]),
@@ -124,6 +131,15 @@ def check_async():
 
 
 def stream_ptr(device=None):
+    """Current stream of `device` as a void*. The kernels launch on the CUDA device that is current in this thread, so the
+    tensors' device must be that device (one process per GPU is the intended deployment): a mismatch fails here, loudly,
+    instead of launching on the wrong GPU."""
+    if device is not None:
+        idx = torch.device(device).index
+        cur = torch.cuda.current_device()
+        if idx is not None and idx != cur:
+            raise AdbError(f"tensors live on cuda:{idx} but the current CUDA device is cuda:{cur}: wrap the call in "
+                           f"`with torch.cuda.device({idx}):` (or call torch.cuda.set_device) — adb200 launches on the current device")
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

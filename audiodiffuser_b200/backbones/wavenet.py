@@ -130,8 +130,10 @@ class WaveNetNoise(nn.Module):
         return self._handle
 
     def parameters_updated(self):
-        """Tell the module its parameters were changed outside torch's version tracking (a fused optimizer step on
-        the flat vector): the packed device weights are rebuilt on the next call."""
+        """Tell the module its parameters were changed outside torch's version tracking: the packed device weights are
+        rebuilt on the next call. REQUIRED after writes through `.data` (`p.data.copy_`, `p.data.mul_`, an EMA weight swap via
+        `.data`, a fused optimizer step on the flat vector) — those do not bump `p._version`, which is what `_param_key`
+        watches; ordinary in-place ops, `load_state_dict` and optimizers do and need nothing."""
         self._handle_key = None
 
     def _free(self):
@@ -220,7 +222,7 @@ class WaveNetNoise(nn.Module):
         return out
 
     def _adb_fused_sample(self, noise, sig, num_steps, sigma_data, s_tmin, s_tmax, s_churn, s_noise, use_heun, alpha,
-                          eps):
+                          eps, churn_seed=0, sample_offset=0):
         if noise.ndim != 3 or noise.shape[1] != 1:
             raise N.AdbError(f"fused DiffWave sampler expects noise [B,1,L]; got {tuple(noise.shape)}")
         B, _, L = noise.shape
@@ -234,10 +236,10 @@ class WaveNetNoise(nn.Module):
             eps = N.require_cuda_f32(eps, "eps")
             if eps.numel() != num_steps * noise.numel():
                 raise N.AdbError(f"eps must have shape [num_steps, *noise.shape]; got {tuple(eps.shape)}")
-        N.check(N.lib().adb_wavenet_sample_edm(h, N.ptr(noise), sig_arr, len(sig), num_steps, sigma_data, s_tmin, s_tmax,
-                                               s_churn, s_noise, int(use_heun), alpha, N.ptr(eps), N.ptr(out), B, L,
-                                               prec, ws, nbytes, ctypes.byref(nfe),
-                                               N.stream_ptr(noise.device)))
+        N.check(N.lib().adb_wavenet_sample_edm_seeded(h, N.ptr(noise), sig_arr, len(sig), num_steps, sigma_data, s_tmin, s_tmax,
+                                                      s_churn, s_noise, int(use_heun), alpha, N.ptr(eps), int(churn_seed),
+                                                      int(sample_offset), N.ptr(out), B, L, prec, ws, nbytes,
+                                                      ctypes.byref(nfe), N.stream_ptr(noise.device)))
         return out, nfe.value
 
     # ---- training step (fused DSM loss forward / backward; fp32 kernels) -----------------------------

@@ -117,13 +117,18 @@ class EluDiffusion(Diffusion):
 
         `noise` (optional, same shape as x) replaces the internal `torch.randn_like(x)`
         (diffusion.py:76) so tests can fix it; by default it is drawn exactly like the reference.
-        With gradients enabled and the fused `WaveNetNoise` as `net`, the returned loss carries an autograd node
-        whose backward runs the CUDA backward pass (training step); otherwise only the value is computed.
+        `x_mask` (bool, broadcastable to x; diffusion.py:80-83): masked-out elements count with weight 0.01. Like the
+        reference, it is also forwarded to `net` with the other kwargs.
+
+        Gradients (the reference trains whatever `net` it is given):
+          * fused `WaveNetNoise`: the loss carries an autograd node whose backward is the CUDA backward pass;
+          * any `net` that PyTorch autograd can differentiate (a reference backbone, any torch module): the net runs under
+            autograd, the loss value and d loss / d F come from the fused kernels (`_GenericDsmLoss`);
+          * a CUDA-kernel backbone without a backward (this package's `UNet1dBase`: sampling only) raises here, at call
+            time, instead of returning a loss that cannot be back-propagated.
         """
         x = N.require_cuda_f32(x, "x")
         N.ensure_device(x.device)
-        if "x_mask" in kwargs:
-            raise NotImplementedError("x_mask loss masking (diffusion.py:80-81) is outside the fused path")
         if self.dynamic_threshold != 0.0:
             raise NotImplementedError("dynamic_threshold != 0 is not supported in the fused loss")
         B, n_per = x.shape[0], x[0].numel()
@@ -131,8 +136,17 @@ class EluDiffusion(Diffusion):
             noise = torch.randn_like(x)
         noise = N.require_cuda_f32(noise, "noise")
         sig, _ = to_batch(B, x.device, xs=sigmas)
+        mask = None
+        if kwargs.get("x_mask") is not None:
+            mask = torch.as_tensor(kwargs["x_mask"], device=x.device).to(torch.bool).expand_as(x).to(torch.uint8).contiguous()
+        wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()) if isinstance(net, nn.Module) \
+            else torch.is_grad_enabled()
         fused_train = getattr(net, "_adb_dsm_loss", None)
-        if fused_train is not None and torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+        if fused_train is not None and wants_grad:
+            if mask is not None:
+                raise NotImplementedError("x_mask with the fused DiffWave training step is not supported (the waveform "
+                                          "module trains on fixed-length clips); compute the loss without gradients or "
+                                          "use a differentiable torch backbone")
             # training step: loss with an autograd node whose backward is the CUDA backward pass
             return fused_train(x, sig.contiguous(), noise, float(self.sigma_data))
         lib, st = N.lib(), N.stream_ptr(x.device)
@@ -141,15 +155,48 @@ class EluDiffusion(Diffusion):
         c_noise = torch.empty(B, dtype=torch.float32, device=x.device)
         N.check(lib.adb_edm_noise_in(N.ptr(x), N.ptr(noise), N.ptr(sig), float(self.sigma_data), N.ptr(x_noisy),
                                      N.ptr(net_in), N.ptr(c_noise), B, n_per, st))
-        with torch.no_grad():
-            if inference:
-                pred = net(net_in, c_noise, cond_drop_prob=0., **kwargs)
-            else:
-                pred = net(net_in, c_noise, **kwargs)
-        pred = N.require_cuda_f32(pred, "net output")
+        if inference:
+            pred = net(net_in, c_noise, cond_drop_prob=0., **kwargs)
+        else:
+            pred = net(net_in, c_noise, **kwargs)
         if pred.shape != x.shape:
             raise N.AdbError(f"net returned {tuple(pred.shape)}, expected {tuple(x.shape)}")
+        if wants_grad and not pred.requires_grad:
+            raise NotImplementedError(
+                f"{type(net).__name__} has trainable parameters but its forward builds no autograd graph: this backbone runs "
+                "on CUDA kernels without a backward pass (UNet1dBase is sampling-only; the fused training step exists for "
+                "WaveNetNoise). Wrap the call in torch.no_grad() for the loss value, or train a PyTorch-differentiable net.")
+        sig_c = sig.contiguous()
+        if pred.requires_grad:
+            return _GenericDsmLoss.apply(pred, x, x_noisy, sig_c, mask, float(self.sigma_data))
+        pred = N.require_cuda_f32(pred, "net output")
         loss = torch.empty(B, dtype=torch.float32, device=x.device)
-        N.check(lib.adb_edm_dsm_loss(N.ptr(x), N.ptr(x_noisy), N.ptr(pred), N.ptr(sig), float(self.sigma_data),
-                                     N.ptr(loss), B, n_per, st))
+        N.check(lib.adb_edm_dsm_loss_masked(N.ptr(x), N.ptr(x_noisy), N.ptr(pred), N.ptr(sig_c), float(self.sigma_data),
+                                            N.ptr(mask), N.ptr(loss), B, n_per, st))
         return loss
+
+
+class _GenericDsmLoss(torch.autograd.Function):
+    """loss[b] of diffusion.py:92-95 on the output F of ANY autograd-capable net: value from adb_edm_dsm_loss_masked,
+    d loss / d F from adb_edm_dsm_loss_grad (one fused pass each); PyTorch carries the gradient on into the net."""
+
+    @staticmethod
+    def forward(ctx, pred, x, x_noisy, sig, mask, sigma_data):
+        f = N.require_cuda_f32(pred.detach(), "net output")
+        B, n_per = x.shape[0], x[0].numel()
+        loss = torch.empty(B, dtype=torch.float32, device=x.device)
+        N.check(N.lib().adb_edm_dsm_loss_masked(N.ptr(x), N.ptr(x_noisy), N.ptr(f), N.ptr(sig), sigma_data, N.ptr(mask),
+                                                N.ptr(loss), B, n_per, N.stream_ptr(x.device)))
+        ctx.save_for_backward(f, x, x_noisy, sig)
+        ctx.mask, ctx.sigma_data = mask, sigma_data
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        f, x, x_noisy, sig = ctx.saved_tensors
+        B, n_per = x.shape[0], x[0].numel()
+        up = N.require_cuda_f32(grad_loss, "grad_loss").reshape(B)
+        d_f = torch.empty_like(f)
+        N.check(N.lib().adb_edm_dsm_loss_grad(N.ptr(x), N.ptr(x_noisy), N.ptr(f), N.ptr(sig), ctx.sigma_data, N.ptr(ctx.mask),
+                                              N.ptr(up), N.ptr(d_f), B, n_per, N.stream_ptr(x.device)))
+        return d_f, None, None, None, None, None

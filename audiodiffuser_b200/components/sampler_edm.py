@@ -33,6 +33,11 @@ def _f32(v: float) -> float:
     return ctypes.c_float(v).value
 
 
+def _draw_seed() -> int:
+    """63-bit seed for the in-kernel churn noise, taken from torch's default CPU generator (so torch.manual_seed governs it)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
 def _fused_target(fn, net):
     diff = getattr(fn, "__self__", None)
     if diff is None or getattr(fn, "__name__", "") != "denoise_fn":
@@ -64,21 +69,29 @@ class EDMSampler(nn.Module):
         return on if (self.s_tmin <= sigma <= self.s_tmax) else 0.0
 
     def step(self, x: Tensor, fn: Callable, net: nn.Module, sigma: float, sigma_next: float, gamma: float,
-             eps: Optional[Tensor] = None, **kwargs) -> Tensor:
-        """One step (sampler_edm.py:333-369). sigma / sigma_next / gamma: python floats or 0-dim tensors."""
+             eps: Optional[Tensor] = None, rng=None, **kwargs) -> Tensor:
+        """One step (sampler_edm.py:333-369). sigma / sigma_next / gamma: python floats or 0-dim tensors.
+
+        The churn noise of a step with gamma > 0 is `eps` when given (parity tests), else it is drawn inside the update
+        kernel (adb_edm_churn_rng) from `rng = (seed, step_index, sample_offset)`; `rng=None` draws a fresh seed from torch's
+        default generator (the reference calls `randn_like(x)` here, sampler_edm.py:346)."""
         sigma, sigma_next, gamma = (_f32(float(v)) for v in (sigma, sigma_next, gamma))
         x = N.require_cuda_f32(x, "x")
         lib, st, n = N.lib(), N.stream_ptr(x.device), x.numel()
-        if eps is None:
-            eps = torch.randn_like(x)                 # drawn every step, like sampler_edm.py:346
         if gamma > 0:
             sigma_hat = _f32(sigma + _f32(gamma * sigma))
             a = _f32(sqrt(_f32(_f32(sigma_hat * sigma_hat) - _f32(sigma * sigma))))
-            eps = N.require_cuda_f32(eps, "eps")
-            noise = torch.empty_like(x)
-            N.check(lib.adb_edm_scale(N.ptr(eps), float(self.s_noise), N.ptr(noise), n, st))
             x_hat = torch.empty_like(x)
-            N.check(lib.adb_edm_axpy(N.ptr(x), N.ptr(noise), a, N.ptr(x_hat), n, st))
+            if eps is not None:
+                eps = N.require_cuda_f32(eps, "eps")
+                noise = torch.empty_like(x)
+                N.check(lib.adb_edm_scale(N.ptr(eps), float(self.s_noise), N.ptr(noise), n, st))
+                N.check(lib.adb_edm_axpy(N.ptr(x), N.ptr(noise), a, N.ptr(x_hat), n, st))
+            else:
+                seed, step_index, sample_offset = rng if rng is not None else (_draw_seed(), 0, 0)
+                B = x.shape[0]
+                N.check(lib.adb_edm_churn_rng(N.ptr(x), N.ptr(x_hat), a, float(self.s_noise), int(seed), int(step_index),
+                                              int(sample_offset), B, n // B, st))
         else:
             sigma_hat, x_hat = sigma, x
         den = N.require_cuda_f32(fn(x_hat, net=net, sigma=sigma_hat, inference=True, cond_scale=self.cond_scale,
@@ -100,11 +113,15 @@ class EDMSampler(nn.Module):
 
     @torch.no_grad()
     def forward(self, noise: Tensor, fn: Callable, net: nn.Module, sigmas: Tensor, eps: Optional[Tensor] = None,
-                **kwargs) -> Tensor:
+                churn_seed: Optional[int] = None, sample_offset: int = 0, **kwargs) -> Tensor:
         """noise [B,C,L] ~ N(0,1), sigmas [N] -> x [B,C,L] (sampler_edm.py:371-397).
 
-        `eps` (optional, [num_steps, *noise.shape]) fixes the churn noise for parity tests; by
-        default one `randn_like(x)` is drawn per step in the reference's order.
+        Churn noise (steps with gamma > 0): by default it is generated INSIDE the update kernel (Philox, keyed by
+        `churn_seed` — drawn from torch's default generator when None, so `torch.manual_seed` makes a run reproducible —
+        and by the global sample index `sample_offset + b`, which makes a waveform independent of batch sharding). Nothing
+        of size [num_steps, *noise.shape] is allocated: the reference draws one `randn_like(x)` per step
+        (sampler_edm.py:346), O(1) memory in the number of steps, and so does this. `eps` (optional,
+        [num_steps, *noise.shape]) supplies the noise explicitly instead (parity tests against the reference).
         """
         noise = N.require_cuda_f32(noise, "noise")
         N.ensure_device(noise.device)
@@ -113,15 +130,19 @@ class EDMSampler(nn.Module):
             raise ValueError(f"schedule has {len(sig)} sigmas but num_steps={self.num_steps} (sampler_edm.py:390)")
         self.last_nfe = 0
         churn = any(self._gamma(s) > 0 for s in sig[:self.num_steps])
-        if eps is None and churn:
-            eps = torch.empty((self.num_steps,) + tuple(noise.shape), dtype=torch.float32, device=noise.device)
-            for i in range(self.num_steps):
-                eps[i].normal_()                      # same RNG consumption as randn_like per step
+        if eps is not None:
+            eps = N.require_cuda_f32(eps, "eps")
+            if eps.numel() != self.num_steps * noise.numel():
+                raise N.AdbError(f"eps must have shape [num_steps, *noise.shape]; got {tuple(eps.shape)}")
+        seed = 0
+        if churn and eps is None:
+            seed = _draw_seed() if churn_seed is None else int(churn_seed)
         diff = _fused_target(fn, net)
         if diff is not None and not kwargs.get("_force_generic", False):
             x, nfe = net._adb_fused_sample(noise, sig, self.num_steps, float(diff.sigma_data), float(self.s_tmin),
                                            float(min(self.s_tmax, 3.0e38)), float(self.s_churn), float(self.s_noise),
-                                           bool(self.use_heun), -1.0, eps if churn else None)
+                                           bool(self.use_heun), -1.0, eps if churn else None, churn_seed=seed,
+                                           sample_offset=sample_offset)
             self.last_nfe = nfe
             return x
         kwargs.pop("_force_generic", None)
@@ -129,11 +150,8 @@ class EDMSampler(nn.Module):
         x = torch.empty_like(noise)
         N.check(N.lib().adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), x.numel(), N.stream_ptr(x.device)))
         for i in range(self.num_steps):
-            e = eps[i] if eps is not None else None
-            if e is None and not churn:
-                e = x                                  # unused when gamma == 0; skip the RNG call
             x = self.step(x, fn=fn, net=net, sigma=sig[i], sigma_next=sig[i + 1], gamma=self._gamma(sig[i]),
-                          eps=e, **kwargs)
+                          eps=eps[i] if eps is not None else None, rng=(seed, i, sample_offset), **kwargs)
         return x
 
 

@@ -246,6 +246,15 @@ extern "C" int adb_pcm16_encode(const float* x, int16_t* pcm, int64_t n, void* s
     return ADB_OK;
 }
 
+extern "C" int adb_edm_churn_rng(const float* x, float* out, float a, float s_noise, uint64_t seed, int step, int64_t sample0,
+                                 int B, int64_t n_per, void* stream) {
+    REQUIRE(x && out && B > 0 && n_per > 0, "adb_edm_churn_rng: bad arguments");
+    REQUIRE(step >= 0 && sample0 >= 0, "adb_edm_churn_rng: step and sample0 must be non-negative");
+    REQUIRE((n_per + 3) / 4 <= 0xFFFFFFFFLL, "adb_edm_churn_rng: sample too long for the 32-bit group counter");
+    KL(1); CK(edm_churn_rng_launch(x, out, a, s_noise, seed, step, sample0, B, n_per, S(stream)));
+    return ADB_OK;
+}
+
 extern "C" int adb_edm_heun_mid(const float* x, const float* f1, float sigma, float sigma_data, float h, float* d, float* x1,
                                 int64_t n, void* stream) {
     REQUIRE(x && f1 && d && x1 && n > 0, "adb_edm_heun_mid: bad arguments");
@@ -280,18 +289,23 @@ extern "C" int adb_edm_noise_in(const float* x, const float* noise, const float*
     return ADB_OK;
 }
 
-extern "C" int adb_edm_dsm_loss(const float* x, const float* x_noisy, const float* f, const float* sigmas,
-                                float sigma_data, float* loss, int B, int64_t n_per, void* stream) {
+extern "C" int adb_edm_dsm_loss_masked(const float* x, const float* x_noisy, const float* f, const float* sigmas,
+                                      float sigma_data, const unsigned char* mask, float* loss, int B, int64_t n_per, void* stream) {
     REQUIRE(x && x_noisy && f && sigmas && loss && B > 0 && n_per > 0, "adb_edm_dsm_loss: bad arguments");
     CK(cudaMemsetAsync(loss, 0, sizeof(float) * B, S(stream)));
     int chunks = static_cast<int>((n_per + 8191) / 8192);
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
     KL(1);
-    edm_dsm_loss_kernel<<<B * chunks, 256, 0, S(stream)>>>(x, x_noisy, f, sigmas, sigma_data, sd2_of(sigma_data), loss,
+    edm_dsm_loss_kernel<<<B * chunks, 256, 0, S(stream)>>>(x, x_noisy, f, sigmas, sigma_data, sd2_of(sigma_data), mask, loss,
                                                            n_per, chunks);
     CK(cudaGetLastError());
     return ADB_OK;
+}
+
+extern "C" int adb_edm_dsm_loss(const float* x, const float* x_noisy, const float* f, const float* sigmas,
+                                float sigma_data, float* loss, int B, int64_t n_per, void* stream) {
+    return adb_edm_dsm_loss_masked(x, x_noisy, f, sigmas, sigma_data, nullptr, loss, B, n_per, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1182,10 +1196,11 @@ static int net_eval(adb_wavenet* n, const float* x, float sigma, float sigma_dat
     return forward_impl(n, x, w.c_noise, w.c_in, 1, f_out, B, L, precision, w, nullptr, nullptr, 0, st);
 }
 
-extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const float* sigmas_host, int n_sigmas,
-                                      int num_steps, float sigma_data, float s_tmin, float s_tmax, float s_churn,
-                                      float s_noise, int use_heun, float alpha, const float* eps, float* x_out, int B, int L,
-                                      int precision, void* ws, int64_t ws_bytes, int* nfe_out, void* stream) {
+extern "C" int adb_wavenet_sample_edm_seeded(adb_wavenet* n, const float* noise, const float* sigmas_host, int n_sigmas,
+                                             int num_steps, float sigma_data, float s_tmin, float s_tmax, float s_churn,
+                                             float s_noise, int use_heun, float alpha, const float* eps, uint64_t churn_seed,
+                                             int64_t sample0, float* x_out, int B, int L, int precision, void* ws,
+                                             int64_t ws_bytes, int* nfe_out, void* stream) {
     int rc = check_forward_args(n, B, L, precision, ws, ws_bytes);
     if (rc) return rc;
     REQUIRE(noise && sigmas_host && x_out, "null tensor argument");
@@ -1209,7 +1224,7 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
     if (!alpha_mode) {
         // gamma_i = min(s_churn / N, sqrt(2) - 1) where s_tmin <= sigma_i <= s_tmax   (sampler_edm.py:383-387)
         const float gamma_on = static_cast<float>(fmin(static_cast<double>(s_churn) / num_steps, sqrt(2.0) - 1.0));
-        if (gamma_on > 0.f) REQUIRE(eps != nullptr, "s_churn > 0 needs the churn-noise tensor eps_dev");
+        REQUIRE(sample0 >= 0, "sample0 must be non-negative");
         for (int i = 0; i < num_steps; ++i) {
             const float sigma = sigmas_host[i];
             const float sigma_next = (i + 1 < n_sigmas) ? sigmas_host[i + 1] : 0.0f;   // t_N = 0 appended (:377)
@@ -1220,10 +1235,15 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
                 sigma_hat = sigma + gs;                                                    // :343
                 const float a = sqrtf(sigma_hat * sigma_hat - sigma * sigma);              // :347
                 ScopedTimer t(n, ADB_TIMER_STEP, st);
-                // x_hat = x + a * (s_noise * eps_i), each product rounded like the reference (:346-347)
-                EdmArgs p = edm_args(x, eps + static_cast<long long>(i) * N, nullptr, x, nullptr, N, N);
-                p.a = a; p.w0 = s_noise;
-                KL(1); CK(edm_launch<OP_CHURN>(p, nullptr, st));
+                // x_hat = x + a * (s_noise * eps_i), each product rounded like the reference (:346-347); eps_i is the caller's
+                // tensor (parity tests) or drawn in the kernel from (churn_seed, sample0 + b, i)
+                if (eps) {
+                    EdmArgs p = edm_args(x, eps + static_cast<long long>(i) * N, nullptr, x, nullptr, N, N);
+                    p.a = a; p.w0 = s_noise;
+                    KL(1); CK(edm_launch<OP_CHURN>(p, nullptr, st));
+                } else {
+                    KL(1); CK(edm_churn_rng_launch(x, x, a, s_noise, churn_seed, i, sample0, B, L, st));
+                }
             }
             rc = net_eval(n, x, sigma_hat, sigma_data, w.fbuf, B, L, precision, w, st);
             if (rc) return rc;
@@ -1292,6 +1312,26 @@ extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const 
     }
     if (x_out != x) CK(cudaMemcpyAsync(x_out, x, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
     if (nfe_out) *nfe_out = nfe;
+    return ADB_OK;
+}
+
+extern "C" int adb_wavenet_sample_edm(adb_wavenet* n, const float* noise, const float* sigmas_host, int n_sigmas,
+                                      int num_steps, float sigma_data, float s_tmin, float s_tmax, float s_churn,
+                                      float s_noise, int use_heun, float alpha, const float* eps, float* x_out, int B, int L,
+                                      int precision, void* ws, int64_t ws_bytes, int* nfe_out, void* stream) {
+    return adb_wavenet_sample_edm_seeded(n, noise, sigmas_host, n_sigmas, num_steps, sigma_data, s_tmin, s_tmax, s_churn, s_noise,
+                                         use_heun, alpha, eps, 0ULL, 0, x_out, B, L, precision, ws, ws_bytes, nfe_out, stream);
+}
+
+// d loss[b] / d F of adb_edm_dsm_loss(_masked), times the per-sample upstream gradient: what autograd needs to carry the DSM
+// loss back into ANY differentiable backbone (generic training path; the fused DiffWave step has its own backward).
+extern "C" int adb_edm_dsm_loss_grad(const float* x, const float* x_noisy, const float* f, const float* sigmas, float sigma_data,
+                                     const unsigned char* mask, const float* upstream, float* d_f, int B, int64_t n_per, void* stream) {
+    REQUIRE(x && x_noisy && f && sigmas && upstream && d_f && B > 0 && n_per > 0, "adb_edm_dsm_loss_grad: bad arguments");
+    KL(1);
+    dsm_loss_bwd_kernel<<<grid_for(static_cast<long long>(B) * n_per), 256, 0, S(stream)>>>(x, x_noisy, f, sigmas, sigma_data,
+                                                                                           sd2_of(sigma_data), 1.0f, d_f, B, n_per, upstream, mask);
+    CK(cudaGetLastError());
     return ADB_OK;
 }
 

@@ -204,10 +204,12 @@ __global__ void edm_cnoise_kernel(const float* __restrict__ sigmas, int sigma_st
 
 // DSM loss (diffusion.py:92-95): loss_b = lambda(sigma_b) * sum_i (D_i - x_i)^2 / n, with
 // D = clamp(c_skip x_noisy + c_out F). One block per (sample, chunk); per-sample atomics finish it.
+// `mask` (optional, one byte per element): the reference's x_mask — masked-out elements count with weight 0.01
+// (diffusion.py:80-83, :92).
 __global__ void __launch_bounds__(256) edm_dsm_loss_kernel(const float* __restrict__ x, const float* __restrict__ x_noisy,
                                                            const float* __restrict__ F, const float* __restrict__ sigmas,
-                                                           float sigma_data, float sd2, float* __restrict__ loss,
-                                                           long long n_per, int chunks) {
+                                                           float sigma_data, float sd2, const unsigned char* __restrict__ mask,
+                                                           float* __restrict__ loss, long long n_per, int chunks) {
     const int b = blockIdx.x / chunks;
     const int ch = blockIdx.x % chunks;
     const float sg = sigmas[b];
@@ -220,7 +222,8 @@ __global__ void __launch_bounds__(256) edm_dsm_loss_kernel(const float* __restri
         const long long g = b * n_per + i;
         const float D = denoised(x_noisy[g], F[g], c.c_skip, c.c_out);
         const float e = D - x[g];
-        acc = fmaf(e, e, acc);
+        const float wgt = (mask == nullptr || mask[g]) ? 1.0f : 0.01f;
+        acc = fmaf(e * e, wgt, acc);
     }
     __shared__ float red[8];
 #pragma unroll
@@ -238,6 +241,83 @@ __global__ void __launch_bounds__(256) edm_dsm_loss_kernel(const float* __restri
             atomicAdd(loss + b, acc * w / static_cast<float>(n_per));
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Churn noise drawn in the kernel (EDMSampler.step: `epsilon = randn_like(x)`, sampler_edm.py:346-347).
+// Counter-based Philox4x32-10 keyed by the trajectory's 64-bit seed; the counter is
+// (group of 4 elements inside the sample, global sample index, sampler step), so a sample's noise depends neither on the
+// batch it is drawn in nor on the rank / world size that owns it, and nothing of size [steps][B][n] ever exists in memory.
+// Normal variates by Box-Muller on 24-bit uniforms: four per Philox block.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                                       uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+        const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+        c1 = static_cast<uint32_t>(p1); c3 = static_cast<uint32_t>(p0); c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// four N(0,1) values of (seed, sample, step, group)
+__device__ __forceinline__ void churn_normals(unsigned long long seed, long long sample, int step, uint32_t group, float (&z)[4]) {
+    uint32_t r[4];
+    philox4x32_10(group, static_cast<uint32_t>(sample), static_cast<uint32_t>(step), static_cast<uint32_t>(static_cast<unsigned long long>(sample) >> 32),
+                  static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = (static_cast<float>(r[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-08f;      // (0, 1), 2^-24 grid
+        const float u2 = static_cast<float>(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;           // [0, 1)
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        z[2 * h] = rad * cs;
+        z[2 * h + 1] = rad * sn;
+    }
+}
+
+// out = x + a * (s_noise * eps), eps ~ N(0,1) from churn_normals; one thread per group of 4 consecutive elements of a sample
+template <bool VEC>
+__global__ void __launch_bounds__(256) edm_churn_rng_kernel(const float* __restrict__ x, float* __restrict__ out, float a, float s_noise,
+                                                            unsigned long long seed, int step, long long sample0, long long n_per,
+                                                            long long groups_per_sample, long long total_groups) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long gidx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; gidx < total_groups; gidx += stride) {
+        const long long b = gidx / groups_per_sample;
+        const long long g = gidx - b * groups_per_sample;
+        float z[4];
+        churn_normals(seed, sample0 + b, step, static_cast<uint32_t>(g), z);
+        const long long base = b * n_per + 4 * g;
+        if (VEC) {
+            const float4 v = *reinterpret_cast<const float4*>(x + base);
+            float4 o;
+            o.x = __fadd_rn(v.x, __fmul_rn(a, __fmul_rn(s_noise, z[0])));
+            o.y = __fadd_rn(v.y, __fmul_rn(a, __fmul_rn(s_noise, z[1])));
+            o.z = __fadd_rn(v.z, __fmul_rn(a, __fmul_rn(s_noise, z[2])));
+            o.w = __fadd_rn(v.w, __fmul_rn(a, __fmul_rn(s_noise, z[3])));
+            *reinterpret_cast<float4*>(out + base) = o;
+        } else {
+            const long long lim = n_per - 4 * g < 4 ? n_per - 4 * g : 4;
+            for (long long k = 0; k < lim; ++k) out[base + k] = __fadd_rn(x[base + k], __fmul_rn(a, __fmul_rn(s_noise, z[k])));
+        }
+    }
+}
+
+inline cudaError_t edm_churn_rng_launch(const float* x, float* out, float a, float s_noise, unsigned long long seed, int step,
+                                        long long sample0, int B, long long n_per, cudaStream_t stream) {
+    const long long gps = (n_per + 3) / 4, total = gps * B;
+    if (total <= 0) return cudaSuccess;
+    const bool vec = (n_per % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (vec) edm_churn_rng_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, out, a, s_noise, seed, step, sample0, n_per, gps, total);
+    else     edm_churn_rng_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, out, a, s_noise, seed, step, sample0, n_per, gps, total);
+    return cudaGetLastError();
 }
 
 template <int OP>

@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(256) inproj_bwd_kernel(const T* __restrict__ d
 __global__ void __launch_bounds__(256) dsm_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x_noisy,
                                                            const float* __restrict__ F, const float* __restrict__ sigmas,
                                                            float sigma_data, float sd2, float upstream, float* __restrict__ dF,
-                                                           int B, long long n_per) {
+                                                           int B, long long n_per, const float* __restrict__ upstream_b = nullptr,
+                                                           const unsigned char* __restrict__ mask = nullptr) {
     const long long total = static_cast<long long>(B) * n_per;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -334,7 +335,9 @@ __global__ void __launch_bounds__(256) dsm_loss_bwd_kernel(const float* __restri
         const float D = clamp1(pre);
         const float lam = (sg * sg + sd2) / ((sg * sigma_data) * (sg * sigma_data));
         const bool pass = pre >= -1.0f && pre <= 1.0f;           // torch.clamp passes the gradient on the closed interval
-        dF[i] = pass ? upstream * 2.0f * lam / static_cast<float>(n_per) * (D - x[i]) * c.c_out : 0.f;
+        const float up = upstream_b ? upstream_b[b] : upstream;                  // per-sample upstream gradient (generic autograd path)
+        const float wgt = (mask == nullptr || mask[i]) ? 1.0f : 0.01f;          // x_mask weights (diffusion.py:80-83)
+        dF[i] = pass ? up * wgt * 2.0f * lam / static_cast<float>(n_per) * (D - x[i]) * c.c_out : 0.f;
     }
 }
 

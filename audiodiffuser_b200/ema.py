@@ -31,8 +31,15 @@ def _flat(net):
     return torch.cat([p.detach().reshape(-1).to(torch.float32) for p in net.parameters()]).contiguous()
 
 
-def _lerp_(ema_flat, net, weight):
-    src = _flat(net)
+def _flat_from_state_dict(net, state):
+    """Flat fp32 vector in parameters() order from a module state_dict (what `state_dict()` of these classes holds)."""
+    dev = next(net.parameters()).device
+    return torch.cat([state[name].detach().reshape(-1).to(device=dev, dtype=torch.float32) for name, _ in net.named_parameters()]).contiguous()
+
+
+def _lerp_(ema_flat, net, weight, flat_params=None):
+    # `flat_params`: the live flat parameter vector when the trainer already keeps one (FusedTrainer.flat) — no re-concatenation
+    src = flat_params if flat_params is not None else _flat(net)
     if not src.is_cuda:
         raise N.AdbError("EMA update needs the network on a B200 (no CPU path)")
     N.check(N.lib().adb_ema_lerp(N.ptr(ema_flat), N.ptr(src), float(weight), ema_flat.numel(), N.stream_ptr(src.device)))
@@ -55,9 +62,10 @@ class PowerFunctionEMA:
     """phema.py:90-123: one EMA copy per relative standard deviation in `stds`."""
 
     @torch.no_grad()
-    def __init__(self, net, stds=[0.050, 0.100]):
+    def __init__(self, net, stds=[0.050, 0.100], flat_params=None):
         self.net = net
         self.stds = stds
+        self.flat_params = flat_params            # optional: the trainer's flat parameter vector, in parameters() order
         self.emas = [_flat(net) for _ in stds]
 
     @torch.no_grad()
@@ -69,7 +77,7 @@ class PowerFunctionEMA:
     def update(self, cur_nimg, batch_size):
         for std, e in zip(self.stds, self.emas):
             beta = power_function_beta(std=std, t_next=cur_nimg, t_delta=batch_size)
-            _lerp_(e, self.net, 1 - float(beta))
+            _lerp_(e, self.net, 1 - float(beta), self.flat_params)
 
     @torch.no_grad()
     def get(self):
@@ -78,15 +86,29 @@ class PowerFunctionEMA:
     def state_dict(self):
         return dict(stds=self.stds, emas=[m.state_dict() for m, _ in self.get()])
 
+    @torch.no_grad()
+    def load_state_dict(self, state):
+        """phema.py:119-123: restore the profiles' relative standard deviations and every EMA copy (a checkpoint resume)."""
+        self.stds = state['stds']
+        flats = [_flat_from_state_dict(self.net, s_ema) for s_ema in state['emas']]
+        if len(flats) != len(self.stds):
+            raise ValueError(f"state holds {len(flats)} EMA copies for {len(self.stds)} stds")
+        if len(flats) == len(self.emas):
+            for e, f in zip(self.emas, flats):
+                e.copy_(f)
+        else:
+            self.emas = flats
+
 
 class TraditionalEMA:
     """phema.py:126-160: half-life EMA with ramp-up."""
 
     @torch.no_grad()
-    def __init__(self, net, halflife_Mimg=float('inf'), rampup_ratio=0.09):
+    def __init__(self, net, halflife_Mimg=float('inf'), rampup_ratio=0.09, flat_params=None):
         self.net = net
         self.halflife_Mimg = halflife_Mimg
         self.rampup_ratio = rampup_ratio
+        self.flat_params = flat_params
         self.ema = _flat(net)
 
     @torch.no_grad()
@@ -99,7 +121,7 @@ class TraditionalEMA:
         if self.rampup_ratio is not None:
             halflife_Mimg = min(halflife_Mimg, cur_nimg / 1e6 * self.rampup_ratio)
         beta = 0.5 ** (batch_size / max(halflife_Mimg * 1e6, 1e-8))
-        _lerp_(self.ema, self.net, 1 - beta)
+        _lerp_(self.ema, self.net, 1 - beta, self.flat_params)
 
     @torch.no_grad()
     def get(self):
@@ -107,3 +129,8 @@ class TraditionalEMA:
 
     def state_dict(self):
         return self.get().state_dict()
+
+    @torch.no_grad()
+    def load_state_dict(self, state):
+        """phema.py:162-163."""
+        self.ema.copy_(_flat_from_state_dict(self.net, state))

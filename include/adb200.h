@@ -64,6 +64,12 @@ int adb_edm_precond_out(const float* x_dev, const float* f_dev, const float* f_n
 int adb_edm_scale(const float* x_dev, float a, float* out_dev, int64_t n, void* stream);
 /* out = x + a * e        (churn: sampler_edm.py:347 with a = sqrt(sigma_hat^2 - sigma^2) * s_noise; also :273, :280) */
 int adb_edm_axpy(const float* x_dev, const float* e_dev, float a, float* out_dev, int64_t n, void* stream);
+/* out[b][i] = x[b][i] + a * (s_noise * eps), eps ~ N(0,1) drawn in the kernel: `epsilon = randn_like(x)` + the churn update of
+ * sampler_edm.py:346-347 in one pass. Philox4x32-10, key = seed, counter = (i / 4, sample0 + b, step, high word of the sample
+ * index), Box-Muller on 24-bit uniforms (oracle/philox.py restates it). Deterministic in (seed, global sample index, step,
+ * element): independent of batch composition, rank and world size. In place (out == x) is allowed. */
+int adb_edm_churn_rng(const float* x_dev, float* out_dev, float a, float s_noise, uint64_t seed, int step, int64_t sample0, int B,
+                      int64_t n_per, void* stream);
 /* d = (x - D) / sigma ; x_next = x + h d          (sampler_edm.py:354-357) */
 int adb_edm_euler(const float* x_dev, const float* denoised_dev, float sigma, float h, float* d_dev,
                   float* x_next_dev, int64_t n, void* stream);
@@ -111,6 +117,16 @@ int adb_edm_noise_in(const float* x_dev, const float* noise_dev, const float* si
 /* loss[b] = lambda(sigma_b) * mean_i (clamp(c_skip x_noisy + c_out F) - x)^2   (diffusion.py:60-63, :92-95) */
 int adb_edm_dsm_loss(const float* x_dev, const float* x_noisy_dev, const float* f_dev, const float* sigmas_dev,
                      float sigma_data, float* loss_dev, int B, int64_t n_per, void* stream);
+/* The same with the reference's `x_mask` (diffusion.py:80-83): mask_dev holds one byte per element of x (already broadcast to
+ * x's shape); elements whose byte is 0 count with weight 0.01. mask_dev == NULL: no mask. */
+int adb_edm_dsm_loss_masked(const float* x_dev, const float* x_noisy_dev, const float* f_dev, const float* sigmas_dev,
+                            float sigma_data, const unsigned char* mask_dev, float* loss_dev, int B, int64_t n_per, void* stream);
+/* d_f[b][i] = upstream[b] * d loss[b] / d F[b][i] of the loss above (torch.clamp passes the gradient on the closed interval): lets
+ * PyTorch autograd carry the DSM loss into ANY differentiable `net` (Diffusion.forward trains whatever backbone it is given,
+ * diffusion.py:65-97); the fused DiffWave training step has its own backward (adb_wavenet_dsm_backward). */
+int adb_edm_dsm_loss_grad(const float* x_dev, const float* x_noisy_dev, const float* f_dev, const float* sigmas_dev,
+                          float sigma_data, const unsigned char* mask_dev, const float* upstream_dev, float* d_f_dev, int B,
+                          int64_t n_per, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DiffWave backbone — src/models/backbones/wavenet.py:153-180 (WaveNetNoise), :117-151, :94-115.
@@ -159,6 +175,16 @@ int adb_wavenet_sample_edm(adb_wavenet* net, const float* noise_dev, const float
                            int num_steps, float sigma_data, float s_tmin, float s_tmax, float s_churn, float s_noise,
                            int use_heun, float alpha, const float* eps_dev, float* x_out_dev, int B, int L,
                            int precision, void* workspace_dev, int64_t workspace_bytes, int* nfe_out, void* stream);
+
+/* The same with the churn noise drawn in the kernel when eps_dev == NULL: Philox4x32-10 keyed by `churn_seed`, counter =
+ * (element group, sample0 + b, step) — `sample0` is the global index of row 0 (the rank's shard offset), so a waveform does
+ * not depend on the batch or world size it is sampled in. Replaces `torch.randn_like(x)` per step (sampler_edm.py:346)
+ * without a [num_steps][B][L] tensor. adb_wavenet_sample_edm == this with churn_seed = 0, sample0 = 0. */
+int adb_wavenet_sample_edm_seeded(adb_wavenet* net, const float* noise_dev, const float* sigmas_host, int n_sigmas,
+                                  int num_steps, float sigma_data, float s_tmin, float s_tmax, float s_churn, float s_noise,
+                                  int use_heun, float alpha, const float* eps_dev, uint64_t churn_seed, int64_t sample0,
+                                  float* x_out_dev, int B, int L, int precision, void* workspace_dev,
+                                  int64_t workspace_bytes, int* nfe_out, void* stream);
 
 /* Per-kernel-class device time of the last *_timed call below (microseconds, CUDA events). */
 #define ADB_TIMER_CONV 0   /* residual-block kernels (the dominant kernel) */

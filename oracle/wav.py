@@ -3,11 +3,13 @@
 The reference calls `torchaudio.save(path, wav[None, :], sample_rate, bits_per_sample=16)`
 (src/models/diffunet_complex_module.py:263-266). torchaudio is a third-party dependency that is absent from this image
 (requirements.txt pins no version; README installs the one matching torch>=2.0), so its published conversion rule is
-restated: the ffmpeg backend (libswresample `av_clip_int16(lrintf(x * (1 << 15)))`) and the sox backend
-(SOX_FLOAT_32BIT_TO_SAMPLE + SOX_SAMPLE_TO_SIGNED_16BIT) both round x * 2^15 to nearest-even and saturate.
-(The soundfile backend scales by 0x7FFF instead; results differ by at most 1 LSB.) PARITY UNPINNED against torchaudio
-itself; pinned against the stdlib `wave` reader (container) and hand-computed known answers (conversion) in
-tests/test_wav_module.py.
+restated: the FFmpeg writer (default backend since torchaudio 2.1) converts with libswresample/audioconvert.c's
+`av_clip_int16(lrintf(x * (1 << 15)))`, i.e. round-half-to-even of x * 2^15, saturated — the rule implemented here. The older
+SoX writer (sox.h SOX_FLOAT_32BIT_TO_SAMPLE, then SOX_SAMPLE_TO_SIGNED_16BIT = add 2^15, shift) rounds exact ties up instead
+and differs by one LSB on odd multiples of 2^-16 only; the soundfile backend scales by 0x7FFF and can differ by 1 LSB anywhere.
+PARITY UNPINNED against torchaudio itself (not runnable here); pinned against an independently assembled fixture (exact
+rational arithmetic + the stdlib `wave` writer, oracle/make_wav_fixture.py -> tests/golden/wav16_fixture.*) and
+hand-computed known answers in tests/test_wav_module.py.
 """
 import numpy as np
 

@@ -90,6 +90,23 @@ def test_ema_classes_gpu_vs_reference_golden():
     m = tr.get()
     assert rel_l2(torch.cat([p.reshape(-1) for p in m.parameters()]), g["trad"]) < 1e-6
     assert [sfx for _, sfx in pf.get()] == ["-0.050", "-0.100"]
+    # checkpoint resume (phema.py:119-123, :162-163): state_dict() -> fresh objects -> load_state_dict() restores every copy,
+    # and the next update continues identically; the state also loads into the reference's own classes when they exist
+    st_pf, st_tr = pf.state_dict(), tr.state_dict()
+    lin2 = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3)).to(dev)
+    pf2, tr2 = PowerFunctionEMA(lin2, stds=[0.3, 0.4]), TraditionalEMA(lin2, halflife_Mimg=0.5, rampup_ratio=0.09)
+    pf2.load_state_dict(st_pf)
+    tr2.load_state_dict(st_tr)
+    assert pf2.stds == [0.05, 0.1]
+    assert all(torch.equal(a, b) for a, b in zip(pf2.emas, pf.emas)) and torch.equal(tr2.ema, tr.ema)
+    lin2.load_state_dict(lin.state_dict())
+    flat = torch.cat([p.detach().reshape(-1) for p in lin.parameters()]).contiguous()
+    pf3 = PowerFunctionEMA(lin2, stds=[0.05, 0.1], flat_params=flat)        # the trainer's flat vector instead of torch.cat per step
+    pf3.load_state_dict(st_pf)
+    pf.update(cur_nimg=nimg + 64, batch_size=64)
+    pf2.update(cur_nimg=nimg + 64, batch_size=64)
+    pf3.update(cur_nimg=nimg + 64, batch_size=64)
+    assert all(torch.equal(a, b) for a, b in zip(pf2.emas, pf.emas)) and all(torch.equal(a, b) for a, b in zip(pf3.emas, pf.emas))
 
 
 def _adpm2_eps(g, B, L, steps):

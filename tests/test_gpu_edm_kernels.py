@@ -182,3 +182,163 @@ def test_fused_heun_mid_post(env, n):
     N.check(lib.adb_edm_heun_post(N.ptr(xd), N.ptr(d), N.ptr(f2d), s1, sd, h, N.ptr(out), n, st))
     N.check_async()
     assert rel_l2(out, want) < 1e-6
+
+
+def test_churn_rng_matches_philox_oracle_and_is_shard_invariant(env):
+    """adb_edm_churn_rng (in-kernel Philox churn noise, replaces randn_like of sampler_edm.py:346): values against the numpy
+    restatement, determinism, and independence of where in a batch / on which shard a sample is drawn."""
+    import numpy as np
+    from oracle.philox import churn_normals
+    N, edm, dev = env
+    lib, st = N.lib(), N.stream_ptr(dev)
+    seed, step = (1 << 61) + 12345, 7
+    for B, n_per, s0 in ((3, 1000, 0), (2, 333, 5), (1, 5, (1 << 33) + 2)):        # vectorised, ragged/unaligned, 64-bit sample index
+        x = _rand((B, n_per), 3).to(dev)
+        out = torch.empty_like(x)
+        N.check(lib.adb_edm_churn_rng(N.ptr(x), N.ptr(out), 0.75, 1.003, seed, step, s0, B, n_per, st))
+        N.check_async()
+        eps = np.stack([churn_normals(seed, s0 + b, step, n_per) for b in range(B)])
+        want = x.cpu().numpy() + np.float32(0.75) * (np.float32(1.003) * eps)
+        assert np.abs(out.cpu().numpy() - want).max() < 2e-5          # Box-Muller through different libm's
+        again = torch.empty_like(x)
+        N.check(lib.adb_edm_churn_rng(N.ptr(x), N.ptr(again), 0.75, 1.003, seed, step, s0, B, n_per, st))
+        assert torch.equal(out, again)
+    # a sample's noise depends on its GLOBAL index only: batch [0, 4) == shards [0, 2) + [2, 4) with sample0 = 2
+    x = torch.zeros(4, 4096, device=dev)
+    full, lo, hi = torch.empty_like(x), torch.empty(2, 4096, device=dev), torch.empty(2, 4096, device=dev)
+    N.check(lib.adb_edm_churn_rng(N.ptr(x), N.ptr(full), 1.0, 1.0, seed, 0, 0, 4, 4096, st))
+    N.check(lib.adb_edm_churn_rng(N.ptr(x), N.ptr(lo), 1.0, 1.0, seed, 0, 0, 2, 4096, st))
+    N.check(lib.adb_edm_churn_rng(N.ptr(x), N.ptr(hi), 1.0, 1.0, seed, 0, 2, 2, 4096, st))
+    N.check_async()
+    assert torch.equal(full[:2], lo) and torch.equal(full[2:], hi)
+    assert not torch.equal(full[0], full[1])
+
+
+def test_churn_rng_statistics(env):
+    """Mean / variance / kurtosis / chi-square of 2^22 in-kernel normals, and no correlation between samples or steps."""
+    N, edm, dev = env
+    lib, st = N.lib(), N.stream_ptr(dev)
+    B, n = 4, 1 << 20
+    zero = torch.zeros(B, n, device=dev)
+    a, b = torch.empty_like(zero), torch.empty_like(zero)
+    N.check(lib.adb_edm_churn_rng(N.ptr(zero), N.ptr(a), 1.0, 1.0, 42, 3, 0, B, n, st))
+    N.check(lib.adb_edm_churn_rng(N.ptr(zero), N.ptr(b), 1.0, 1.0, 42, 4, 0, B, n, st))
+    N.check_async()
+    z = a.double().flatten()
+    m = z.numel()
+    assert abs(float(z.mean())) < 4 / math.sqrt(m)
+    assert abs(float(z.var()) - 1.0) < 4 * math.sqrt(2.0 / m)
+    assert abs(float((z ** 4).mean()) - 3.0) < 4 * math.sqrt(96.0 / m)
+    edges = torch.tensor([-1e9, -2.5, -2.0, -1.5, -1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0, 2.5, 1e9], dtype=torch.float64, device=dev)
+    obs = torch.histogram(z.cpu(), bins=edges.cpu())[0]
+    cdf = 0.5 * (1 + torch.erf(edges.cpu() / math.sqrt(2)))
+    exp = (cdf[1:] - cdf[:-1]) * m
+    chi2 = float(((obs - exp) ** 2 / exp).sum())
+    assert chi2 < 40.0, chi2                                           # 11 degrees of freedom: P(chi2 > 40) ~ 4e-5
+    for u, v in ((a[0], a[1]), (a[0], b[0]), (a[2, :-1], a[2, 1:])):       # across samples, across steps, neighbouring elements
+        r = float((u.double() * v.double()).mean())
+        assert abs(r) < 5 / math.sqrt(u.numel()), r
+
+
+def test_default_sampler_churn_needs_no_eps_tensor(env):
+    """EDMSampler with the reference's default churn (s_churn = 150) and no `eps`: fused trajectory and generic Python loop
+    draw the same in-kernel noise (same seed) and agree; the result is reproducible under torch.manual_seed, depends on the
+    seed, and is invariant to sharding the batch (sample_offset). No [num_steps, B, C, L] tensor is involved."""
+    N, edm, dev = env
+    from audiodiffuser_b200 import EluDiffusion, EDMSampler, KarrasSchedule, WaveNetNoise
+    from oracle.weights import make_wavenet_state_dict
+    net = WaveNetNoise(64, 3, 2, precision="fp32")
+    net.load_state_dict(make_wavenet_state_dict(64, 3, seed=3), strict=True)
+    net = net.to(dev)
+    diff = EluDiffusion(0.2)
+    steps = 6
+    sig = KarrasSchedule(0.002, 80.0, 7.0, steps)().to(dev)
+    noise = _rand((4, 1, 500), 21).to(dev)
+    smp = EDMSampler(num_steps=steps)                                  # reference defaults: s_churn = 150, s_noise = 1.04
+    fused = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=99)
+    generic = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=99, _force_generic=True)
+    N.check_async()
+    assert rel_l2(fused, generic) < 1e-5, rel_l2(fused, generic)
+    assert rel_l2(smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=100), fused) > 1e-2
+    halves = torch.cat([smp(noise[:2].contiguous(), fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=99),
+                        smp(noise[2:].contiguous(), fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=99, sample_offset=2)])
+    assert rel_l2(halves, fused) < 1e-6, rel_l2(halves, fused)
+    torch.manual_seed(5)
+    r1 = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig)
+    torch.manual_seed(5)
+    r2 = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig)
+    assert torch.equal(r1, r2) and not torch.equal(r1, fused)
+    # a churn window that contains no sigma: s_churn > 0 but no step draws noise (was a spurious "needs eps" error)
+    quiet = EDMSampler(s_tmin=1e3, s_tmax=1e4, s_churn=30.0, num_steps=steps)
+    plain = EDMSampler(s_churn=0.0, num_steps=steps)
+    assert torch.equal(quiet(noise, fn=diff.denoise_fn, net=net, sigmas=sig), plain(noise, fn=diff.denoise_fn, net=net, sigmas=sig))
+
+
+def test_dsm_loss_x_mask_and_generic_autograd(env):
+    """Diffusion.forward on an arbitrary differentiable torch net (diffusion.py:65-97 trains whatever net it gets): the loss
+    value with and without x_mask against the oracle formula, and the gradients that reach the net's parameters through
+    _GenericDsmLoss against PyTorch autograd of the same loss written in torch ops."""
+    N, edm, dev = env
+    from audiodiffuser_b200 import EluDiffusion
+    torch.manual_seed(0)
+    B, C, L = 3, 2, 257
+    net_mod = torch.nn.Conv1d(C, C, 5, padding=2).to(dev)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = net_mod
+
+        def forward(self, x, t, **kw):
+            return self.conv(x) * (1.0 + 0.1 * t.view(-1, 1, 1))
+
+    net = Net()
+    diff = EluDiffusion(sigma_data=0.2)
+    x = (_rand((B, C, L), 5) * 0.3).to(dev)
+    noise = _rand((B, C, L), 6).to(dev)
+    sig = torch.tensor([0.05, 0.7, 9.0], device=dev)
+    mask = (torch.arange(L, device=dev)[None, None, :] < torch.tensor([257, 100, 31], device=dev)[:, None, None])   # [B,1,L] padding mask
+
+    def torch_loss(m):
+        sp = sig.view(-1, 1, 1)
+        xn = x + sp * noise
+        sd = 0.2
+        c_skip = sd ** 2 / (sp ** 2 + sd ** 2)
+        c_out = sp * sd * (sd ** 2 + sp ** 2) ** -0.5
+        c_in = (sp ** 2 + sd ** 2) ** -0.5
+        den = (c_skip * xn + c_out * net(c_in * xn, torch.log(sig) * 0.25)).clamp(-1, 1)
+        w = torch.ones_like(x) if m is None else (torch.ones_like(x) * m + torch.ones_like(x) * (~m) * 0.01)
+        lam = (sig ** 2 + sd ** 2) * (sig * sd) ** -2
+        return ((den - x) ** 2 * w).flatten(1).sum(1) * lam / (C * L)
+
+    for m in (None, mask):
+        kw = {} if m is None else {"x_mask": m}
+        net.zero_grad()
+        want = torch_loss(m)
+        want.mean().backward()
+        gw, gb = net.conv.weight.grad.clone(), net.conv.bias.grad.clone()
+        with torch.no_grad():
+            val = diff(x, net, sigmas=sig, noise=noise, **kw)
+        assert not val.requires_grad and rel_l2(val, want) < 1e-5, rel_l2(val, want)
+        net.zero_grad()
+        got = diff(x, net, sigmas=sig, noise=noise, **kw)
+        assert got.requires_grad and rel_l2(got, want) < 1e-5
+        got.mean().backward()
+        assert rel_l2(net.conv.weight.grad, gw) < 1e-4, rel_l2(net.conv.weight.grad, gw)
+        assert rel_l2(net.conv.bias.grad, gb) < 1e-4
+    N.check_async()
+
+
+def test_kernel_backbone_without_backward_raises_at_call_time(env):
+    """A CUDA-kernel backbone with parameters but no backward pass (UNet1dBase is sampling-only) must refuse a training call
+    when it is made, not hand back a loss that fails later in .backward()."""
+    N, edm, dev = env
+    from audiodiffuser_b200 import EluDiffusion, UNet1dBase
+    from oracle.weights import UNET_SMALL
+    net = UNet1dBase(precision="fp32", **UNET_SMALL).to(dev)
+    diff = EluDiffusion(0.2)
+    x = _rand((1, 2, 256), 1).to(dev)
+    with pytest.raises(NotImplementedError, match="sampling-only"):
+        diff(x, net, sigmas=torch.tensor([0.5], device=dev))
+    with torch.no_grad():
+        assert diff(x, net, sigmas=torch.tensor([0.5], device=dev)).shape == (1,)

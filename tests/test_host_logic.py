@@ -174,3 +174,19 @@ def test_shard_noise_invariant_to_world_size():
         parts = torch.cat([shard_noise(10, r, world, length=33, base_seed=5) for r in range(world)])
         assert torch.equal(parts, full)
     assert not torch.equal(full[0], full[1])
+
+
+def test_philox_oracle_known_answers():
+    """oracle/philox.py (the CPU restatement of the in-kernel churn-noise generator) against the Random123 known-answer
+    vectors of Philox4x32-10, and the moments of the normal variates it derives."""
+    import numpy as np
+    from oracle.philox import churn_normals, philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(v) for v in philox4x32_10(*ctr, *key)) == want
+    z = churn_normals(seed=77, sample=3, step=5, n_per=1 << 18).astype(np.float64)
+    assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 0.02 and abs((z ** 4).mean() - 3) < 0.1
+    assert not np.array_equal(z[:16], churn_normals(77, 4, 5, 16)) and not np.array_equal(z[:16], churn_normals(77, 3, 6, 16))
+    assert np.array_equal(z[:1001].astype(np.float32), churn_normals(77, 3, 5, 1001))         # ragged length: same stream, truncated

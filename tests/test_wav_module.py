@@ -27,6 +27,24 @@ def test_pcm16_oracle_known_answers():
     assert pcm16(x).tolist() == want
 
 
+def test_wav16_fixture_exact_rational_rule_and_stdlib_container(tmp_path):
+    """tests/golden/wav16_fixture.*: ties on both sides of zero, +-1, beyond full scale, +-inf, NaN, denormals — integers from
+    exact rational arithmetic, file assembled by the standard library's wave writer (oracle/make_wav_fixture.py). The oracle
+    encoder must reproduce the integers, and this package's RIFF writer must reproduce the file byte for byte."""
+    from audiodiffuser_b200.wav import write_wav16
+    from oracle.wav import pcm16, read_wav16
+    g = np.load(os.path.join(ROOT, "tests", "golden", "wav16_fixture.npz"))
+    assert np.array_equal(pcm16(g["x"]), g["pcm"])
+    frames = g["pcm"].size // 2
+    stereo = g["pcm"][:2 * frames].reshape(2, frames)
+    path = str(tmp_path / "mine.wav")
+    write_wav16(path, torch.from_numpy(stereo.copy()), 16000)
+    with open(path, "rb") as a, open(os.path.join(ROOT, "tests", "golden", "wav16_fixture.wav"), "rb") as b:
+        assert a.read() == b.read()
+    data, sr = read_wav16(os.path.join(ROOT, "tests", "golden", "wav16_fixture.wav"))
+    assert sr == 16000 and np.array_equal(data, stereo)
+
+
 def test_wav16_container_roundtrip(tmp_path):
     from audiodiffuser_b200.wav import wav16_header, write_wav16
     from oracle.wav import read_wav16
@@ -110,6 +128,16 @@ def test_module_config_instantiates_and_backbone_copies():
 
 
 # ---------------------------------------------------------------- GPU ----------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.gpu
+def test_pcm16_kernel_matches_fixture():
+    """The CUDA encoder on the committed fixture vector (ties, saturation, +-inf, NaN): bit-exact."""
+    from audiodiffuser_b200.wav import pcm16_encode
+    g = np.load(os.path.join(ROOT, "tests", "golden", "wav16_fixture.npz"))
+    got = pcm16_encode(torch.from_numpy(g["x"]).cuda()).cpu().numpy()
+    assert np.array_equal(got, g["pcm"])
+
+
 @pytest.mark.gpu
 def test_pcm16_kernel_bit_exact():
     from audiodiffuser_b200.wav import pcm16_encode
