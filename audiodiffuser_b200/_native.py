@@ -44,6 +44,7 @@ _SIGS = {
     "adb_pcm16_encode": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "adb_edm_heun_mid": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "adb_edm_heun_post": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_int64, c_void_p]),
+    "adb_edm_euler_raw": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_int64, c_void_p]),
     "adb_edm_noise_in": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64,
                                  c_void_p]),
     "adb_edm_dsm_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int64, c_void_p]),

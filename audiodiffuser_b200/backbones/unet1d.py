@@ -547,6 +547,100 @@ class UNet1dBase(nn.Module):
         self.graph_launches += per_replay
         return so.clone()
 
+    # ---- device-resident EDM trajectory (EDMSampler.forward, sampler_edm.py:371-397) ---------------------------------------
+    def _trajectory_graphs(self, B: int, L: int, dev, sigma_data: float):
+        """Static state buffers + two CUDA graphs of one network evaluation each, F = net(c_in(sigma) x, c_noise(sigma)):
+        graph 0 reads the state x, graph 1 the Heun midpoint x1; sigma lives in a 1-element device buffer that the loop
+        rewrites before each replay. Nothing is copied in or out per evaluation (the plain forward() replay copies x in
+        and clones F out: two 2 x 268 MB passes per evaluation at config 4)."""
+        key = ("traj", B, L, dev.index, float(sigma_data))
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        cin = self.cfg["in_channels"]
+        lib = N.lib()
+        buf = {k: torch.empty(B, cin, L, dtype=torch.float32, device=dev) for k in ("x", "x1", "d", "F", "net_in")}
+        buf["c_noise"] = torch.empty(B, dtype=torch.float32, device=dev)
+        buf["sigma"] = torch.ones(1, dtype=torch.float32, device=dev)
+        buf["one"] = torch.ones(1, dtype=torch.float32, device=dev)
+        buf["x"].zero_()
+        buf["x1"].zero_()
+
+        def evaluate(src):
+            N.check(lib.adb_edm_precond_in(N.ptr(src), N.ptr(buf["sigma"]), 0, float(sigma_data), N.ptr(buf["net_in"]),
+                                           N.ptr(buf["c_noise"]), B, cin * L, N.stream_ptr(dev)))
+            self._run(buf["net_in"], buf["c_noise"], buf["F"])
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            evaluate(buf["x"])                                   # warm-up outside capture (tensor-map cache, attributes)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graphs, per_replay = [], 0
+        for src in ("x", "x1"):
+            graph = torch.cuda.CUDAGraph()
+            before = lib.adb_launch_count(0)
+            with torch.cuda.graph(graph, pool=graphs[0].pool() if graphs else None):
+                evaluate(buf[src])
+            per_replay = lib.adb_launch_count(0) - before
+            graphs.append(graph)
+        g = self._graphs[key] = (buf, graphs, per_replay)
+        return g
+
+    @torch.no_grad()
+    def _adb_fused_sample(self, noise, sig, num_steps, sigma_data, s_tmin, s_tmax, s_churn, s_noise, use_heun, alpha, eps,
+                          churn_seed=0, sample_offset=0):
+        """EDM Heun / Euler + churn trajectory for the unconditional U-Net with the state resident in static buffers: per step
+        [churn kernel] -> graph replay -> fused mid kernel -> graph replay -> fused post kernel (48 B of HBM traffic per state
+        element and Heun step around the network). Returns None when this mode does not apply (the caller then runs the generic
+        Python loop): class-conditioned nets, the alpha sampler, eager mode, differing in/out channel counts."""
+        cfg = self.cfg
+        if alpha > 0 or cfg["class_cond"] or not self.use_cuda_graph or (cfg.get("out_channels") or cfg["in_channels"]) != cfg["in_channels"]:
+            return None
+        from math import sqrt
+        from ..components.sampler_edm import _f32
+        B, cin, L = noise.shape
+        dev = noise.device
+        self._pack()
+        buf, graphs, per_replay = self._trajectory_graphs(B, L, dev, sigma_data)
+        lib, st, n = N.lib(), N.stream_ptr(dev), noise.numel()
+        x, x1, d, F = buf["x"], buf["x1"], buf["d"], buf["F"]
+
+        def evaluate(which, sigma):
+            N.check(lib.adb_edm_scale(N.ptr(buf["one"]), float(sigma), N.ptr(buf["sigma"]), 1, st))
+            graphs[which].replay()
+            self.graph_launches += per_replay
+
+        N.check(lib.adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), n, st))
+        gamma_on = _f32(min(s_churn / num_steps, sqrt(2) - 1))
+        nfe = 0
+        for i in range(num_steps):
+            sigma = _f32(sig[i])
+            sigma_next = _f32(sig[i + 1]) if i + 1 < len(sig) else 0.0
+            gamma = gamma_on if (s_tmin <= sigma <= s_tmax) else 0.0
+            sigma_hat = sigma
+            if gamma > 0:
+                sigma_hat = _f32(sigma + _f32(gamma * sigma))
+                a = _f32(sqrt(_f32(_f32(sigma_hat * sigma_hat) - _f32(sigma * sigma))))
+                if eps is not None:
+                    tmp = torch.empty_like(x)
+                    N.check(lib.adb_edm_scale(N.ptr(eps[i]), float(s_noise), N.ptr(tmp), n, st))
+                    N.check(lib.adb_edm_axpy(N.ptr(x), N.ptr(tmp), a, N.ptr(x), n, st))
+                else:
+                    N.check(lib.adb_edm_churn_rng(N.ptr(x), N.ptr(x), a, float(s_noise), int(churn_seed), i, int(sample_offset), B,
+                                                  cin * L, st))
+            evaluate(0, sigma_hat)
+            nfe += 1
+            h = _f32(sigma_next - sigma_hat)
+            if sigma_next != 0 and use_heun:
+                N.check(lib.adb_edm_heun_mid(N.ptr(x), N.ptr(F), sigma_hat, float(sigma_data), h, N.ptr(d), N.ptr(x1), n, st))
+                evaluate(1, sigma_next)
+                nfe += 1
+                N.check(lib.adb_edm_heun_post(N.ptr(x), N.ptr(d), N.ptr(F), sigma_next, float(sigma_data), h, N.ptr(x), n, st))
+            else:
+                N.check(lib.adb_edm_euler_raw(N.ptr(x), N.ptr(F), sigma_hat, float(sigma_data), h, N.ptr(x), n, st))
+        return x.clone(), nfe
+
     @torch.no_grad()
     def _adb_cfg_pair(self, x: Tensor, t: Tensor, classes: Tensor):
         """Classifier-free guidance pair in ONE network evaluation of batch 2B (diffusion.py:50-53 calls the net twice):

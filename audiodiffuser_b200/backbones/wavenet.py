@@ -76,6 +76,8 @@ class _ResidualGroup(nn.Module):
 
 
 class WaveNetNoise(nn.Module):
+    _adb_unconditional = True           # no conditioning input: guidance / conditioning kwargs cannot change the output
+
     def __init__(self, residual_channels: int = 256, residual_layers: int = 36, dilation_cycle: int = 12,
                  precision: str = "bf16"):
         super().__init__()
@@ -162,6 +164,12 @@ class WaveNetNoise(nn.Module):
         key = (device, prec)
         ent = self._ws.get(key)
         if ent is None or ent[2] < need:
+            if ent is not None:
+                # growing: release the old buffer first (the z stash alone is ~75 GB at 256-sample passes; two of them do
+                # not fit) and hand its block back to the driver so the larger request is not a second allocation
+                self._ws.pop(key)
+                del ent
+                torch.cuda.empty_cache()
             buf, p = N.alloc_workspace(need, device)
             self._ws[key] = ent = (buf, p, need)
         return ent[1], need

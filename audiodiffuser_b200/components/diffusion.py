@@ -139,8 +139,8 @@ class EluDiffusion(Diffusion):
         mask = None
         if kwargs.get("x_mask") is not None:
             mask = torch.as_tensor(kwargs["x_mask"], device=x.device).to(torch.bool).expand_as(x).to(torch.uint8).contiguous()
-        wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()) if isinstance(net, nn.Module) \
-            else torch.is_grad_enabled()
+        # a plain callable has no parameters of its own: whether a graph is needed shows on its output (pred.requires_grad)
+        wants_grad = torch.is_grad_enabled() and isinstance(net, nn.Module) and any(p.requires_grad for p in net.parameters())
         fused_train = getattr(net, "_adb_dsm_loss", None)
         if fused_train is not None and wants_grad:
             if mask is not None:

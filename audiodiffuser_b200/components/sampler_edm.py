@@ -138,14 +138,17 @@ class EDMSampler(nn.Module):
         if churn and eps is None:
             seed = _draw_seed() if churn_seed is None else int(churn_seed)
         diff = _fused_target(fn, net)
-        if diff is not None and not kwargs.get("_force_generic", False):
-            x, nfe = net._adb_fused_sample(noise, sig, self.num_steps, float(diff.sigma_data), float(self.s_tmin),
-                                           float(min(self.s_tmax, 3.0e38)), float(self.s_churn), float(self.s_noise),
-                                           bool(self.use_heun), -1.0, eps if churn else None, churn_seed=seed,
-                                           sample_offset=sample_offset)
-            self.last_nfe = nfe
-            return x
-        kwargs.pop("_force_generic", None)
+        force_generic = kwargs.pop("_force_generic", False)
+        # device-resident trajectory: the unconditional call (no conditioning kwargs, no guidance); a backbone may decline (None)
+        uncond = getattr(net, "_adb_unconditional", False)      # DiffWave: conditioning kwargs / guidance cannot change its output
+        if diff is not None and not force_generic and (uncond or (not kwargs and self.cond_scale == 1.0)):
+            res = net._adb_fused_sample(noise, sig, self.num_steps, float(diff.sigma_data), float(self.s_tmin),
+                                        float(min(self.s_tmax, 3.0e38)), float(self.s_churn), float(self.s_noise),
+                                        bool(self.use_heun), -1.0, eps if churn else None, churn_seed=seed,
+                                        sample_offset=sample_offset)
+            if res is not None:
+                x, self.last_nfe = res
+                return x
         sig = sig + [0.0]                              # t_N = 0 (sampler_edm.py:377)
         x = torch.empty_like(noise)
         N.check(N.lib().adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), x.numel(), N.stream_ptr(x.device)))
@@ -204,12 +207,14 @@ class EDMAlphaSampler(nn.Module):
             raise ValueError(f"schedule has {len(sig)} sigmas but num_steps={self.num_steps}")
         self.last_nfe = 0
         diff = _fused_target(fn, net)
-        if diff is not None and not kwargs.get("_force_generic", False):
-            x, nfe = net._adb_fused_sample(noise, sig, self.num_steps, float(diff.sigma_data), 0.0, 3.0e38, 0.0, 1.0,
-                                           bool(self.use_heun), float(self.alpha), None)
-            self.last_nfe = nfe
-            return x
-        kwargs.pop("_force_generic", None)
+        force_generic = kwargs.pop("_force_generic", False)
+        uncond = getattr(net, "_adb_unconditional", False)
+        if diff is not None and not force_generic and (uncond or (not kwargs and self.cond_scale == 1.0)):
+            res = net._adb_fused_sample(noise, sig, self.num_steps, float(diff.sigma_data), 0.0, 3.0e38, 0.0, 1.0,
+                                        bool(self.use_heun), float(self.alpha), None)
+            if res is not None:
+                x, self.last_nfe = res
+                return x
         x = torch.empty_like(noise)
         N.check(N.lib().adb_edm_scale(N.ptr(noise), sig[0], N.ptr(x), x.numel(), N.stream_ptr(x.device)))
         for i in range(self.num_steps - 1):

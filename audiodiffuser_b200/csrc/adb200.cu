@@ -275,6 +275,16 @@ extern "C" int adb_edm_heun_post(const float* x, const float* d, const float* f2
     return ADB_OK;
 }
 
+extern "C" int adb_edm_euler_raw(const float* x, const float* f, float sigma, float sigma_data, float h, float* x_next, int64_t n,
+                                 void* stream) {
+    REQUIRE(x && f && x_next && n > 0, "adb_edm_euler_raw: bad arguments");
+    const PrecondCoef c = precond_coef(sigma, sigma_data, sd2_of(sigma_data));
+    EdmArgs p = edm_args(x, f, nullptr, x_next, nullptr, n, n);
+    p.s0 = sigma; p.h = h; p.c_skip0 = c.c_skip; p.c_out0 = c.c_out;
+    KL(1); CK(edm_launch<OP_EULER_RAW>(p, nullptr, S(stream)));
+    return ADB_OK;
+}
+
 extern "C" int adb_edm_noise_in(const float* x, const float* noise, const float* sigmas, float sigma_data, float* x_noisy,
                                 float* net_in, float* c_noise, int B, int64_t n_per, void* stream) {
     REQUIRE(x && noise && sigmas && x_noisy && net_in && B > 0 && n_per > 0, "adb_edm_noise_in: bad arguments");

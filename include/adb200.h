@@ -107,6 +107,10 @@ int adb_edm_heun_mid(const float* x_dev, const float* f1_dev, float sigma, float
                      float* x1_dev, int64_t n, void* stream);
 int adb_edm_heun_post(const float* x_dev, const float* d_dev, const float* f2_dev, float sigma1, float sigma_data, float h,
                       float* x_next_dev, int64_t n, void* stream);
+/* Final / Euler-only step on the RAW network output: D = clamp(c_skip x + c_out F) ; x_next = x + h (x - D) / sigma
+ * (sampler_edm.py:354-357 with diffusion.py:46-63 folded in; 12 B per element; x_next may alias x). */
+int adb_edm_euler_raw(const float* x_dev, const float* f_dev, float sigma, float sigma_data, float h, float* x_next_dev, int64_t n,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training twin — src/models/components/diffusion.py:65-97 (Diffusion.forward).

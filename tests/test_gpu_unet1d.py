@@ -150,3 +150,31 @@ def test_attention_kernels_vs_fp64_softmax_attention(dev, L, monkeypatch):
     assert rel_l2(ref, want) < 4e-3
     assert rel_l2(got, ref) < 6e-3
     assert rel_l2(run(0, q.float(), kv.float()), want) < 1e-5              # fp32 kernel
+
+
+@pytest.mark.parametrize("precision,churn", [("fp32", 0.0), ("bf16", 0.0), ("fp32", 40.0)])
+def test_unet_device_resident_trajectory_matches_generic_loop(dev, precision, churn):
+    """UNet1dBase._adb_fused_sample (state in static buffers, two CUDA graphs, fused mid / post kernels) against the generic
+    Python loop of the same sampler and against the reference golden: same arithmetic, so fp32 agrees to round-off."""
+    from audiodiffuser_b200 import EluDiffusion, EDMSampler, _native as N
+    from oracle.weights import UNET_MID
+    g = load_golden("unet1d_mid_edm")
+    B, L, seed, steps = (int(v) for v in g["cfg"])
+    net = make_unet(UNET_MID, seed, precision, dev)
+    diff = EluDiffusion(0.2)
+    noise = torch.from_numpy(g["noise"]).to(dev)
+    sig = torch.from_numpy(g["sigmas"]).to(dev)
+    smp = EDMSampler(s_churn=churn, s_noise=1.003, num_steps=steps)
+    fused = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=7)
+    nfe = smp.last_nfe
+    generic = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=7, _force_generic=True)
+    N.check_async()
+    assert nfe == smp.last_nfe == 2 * steps - 1
+    assert ("traj", B, L, dev.index, 0.2) in net._graphs                      # the device-resident path really ran
+    e = rel_l2(fused, generic)
+    record_parity(f"unet1d_fused_trajectory_vs_generic_{precision}_churn{churn}", rel_l2=e)
+    assert e < (2e-6 if precision == "fp32" else 5e-3), e
+    if churn == 0.0:
+        assert rel_l2(fused, g["heun"]) < (5e-6 if precision == "fp32" else 1e-2)
+    again = smp(noise, fn=diff.denoise_fn, net=net, sigmas=sig, churn_seed=7)
+    assert torch.equal(again, fused)                                        # static buffers are fully rewritten per call
