@@ -915,8 +915,11 @@ static int sm_count() {
 // bf16 sampling path with the z-stash kernel (wavenet_tc3.cuh): the batch is processed in passes of w.Bc samples; every
 // block leaves its gated activations in the stash and one skip GEMM per w.G blocks contracts them into the fp32 skip sum.
 // `emb` ([B][512], embed_mlp_kernel) is already in w.emb.
+// Training forward (h_save / y_save non-null, one pass over the whole batch): block l reads h_save slot l and writes slot l + 1, and
+// leaves its pre-gate activations in y_save slot l; the stash then holds every block's z (w.G == layers).
 static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale, int in_scale_stride, float* out, int B, int L,
-                           const Workspace& w, cudaStream_t st) {
+                           const Workspace& w, cudaStream_t st, __nv_bfloat16* h_save = nullptr, __nv_bfloat16* y_save = nullptr) {
+    REQUIRE(!h_save || (w.Bc == B && w.G == n->layers), "internal: the training forward needs a whole-batch workspace with a full stash");
     const int C = n->C, layers = n->layers;
     const int num_sms = sm_count();
     const int tiles_per_b = (L + TC_TILE_T - 1) / TC_TILE_T;
@@ -933,7 +936,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
             CK(conv_cl_f32(a, st));
             in_proj_kernel<true><<<grid_for(BL * (C / 8)), 256, 0, st>>>(
                 x + static_cast<long long>(b0) * L, in_scale ? in_scale + static_cast<long long>(b0) * in_scale_stride : nullptr,
-                in_scale_stride, n->w_in_f, n->b_in, w.hbA, bc, L, C);
+                in_scale_stride, n->w_in_f, n->b_in, h_save ? h_save : w.hbA, bc, L, C);
             CK(cudaGetLastError());
         }
         const int num_tiles = tiles_per_b * bc;
@@ -950,7 +953,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
         if (!rc) rc = get_act_map(n, w.stash, w.G * bc, L, 0, &m_zld);
         if (!rc) rc = get_act_map(n, w.skip, bc, L, 2, &m_skip);
         if (rc) return rc;
-        __nv_bfloat16 *hin = w.hbA, *hout = w.hbB;
+        __nv_bfloat16 *hin = h_save ? h_save : w.hbA, *hout = (h_save && layers > 1) ? h_save + BL * C : w.hbB;
         for (int l = 0; l < layers; ++l) {
             const int slot = l % w.G;
             {
@@ -961,6 +964,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 if (rc) return rc;
                 BlockZsParams bp;
                 bp.E = w.E; bp.b2 = n->L[l].b2; bp.h_in = hin; bp.h_out_dbg = hout;
+                bp.y_out = y_save ? y_save + static_cast<long long>(l) * BL * 2 * C : nullptr;
                 bp.B = bc; bp.L = L; bp.layer = l; bp.layers = layers; bp.dil = 1 << (l % n->cycle);
                 bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
                 bp.write_h = (l + 1 < layers) ? 1 : 0;
@@ -970,7 +974,8 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true>, m_h, n->tm_w2, m_hout, m_zst, bp));
                 else            CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false>, m_h, n->tm_w2, m_hout, m_zst, bp));
             }
-            { __nv_bfloat16* tmp = hin; hin = hout; hout = tmp; }
+            if (h_save) { hin = hout; hout = (l + 2 < layers) ? hin + BL * C : w.hbB; }
+            else { __nv_bfloat16* tmp = hin; hin = hout; hout = tmp; }
             if (slot == w.G - 1 || l + 1 == layers) {
                 ScopedTimer t(n, ADB_TIMER_SKIP, st);
                 SkipGemmParams sp;
@@ -998,8 +1003,9 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
 
 static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, const float* in_scale, int in_scale_stride,
                         float* out, int B, int L, int precision, const Workspace& w, float* dump_h, float* dump_skip,
-                        int dump_layers, cudaStream_t st, __nv_bfloat16* h_save = nullptr) {
-    // h_save (bf16 path, training): [layers][B][L][C]; block l reads slot l and writes slot l + 1 instead of ping-ponging
+                        int dump_layers, cudaStream_t st, __nv_bfloat16* h_save = nullptr, __nv_bfloat16* y_save = nullptr) {
+    // h_save (bf16 path, training): [layers][B][L][C]; block l reads slot l and writes slot l + 1 instead of ping-ponging.
+    // y_save (z-stash path, training): [layers][B][L][2C], every block's pre-gate activations, so the backward recomputes nothing.
     const int C = n->C, layers = n->layers;
     const long long BL = static_cast<long long>(B) * L;
     {
@@ -1054,8 +1060,8 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
     }
 
     // ---------------- bf16 tensor-core path ----------------
-    if (!h_save && dump_layers == 0 && n->block_kernel == 3)
-        return forward_bf16_zs(n, x, in_scale, in_scale_stride, out, B, L, w, st);
+    if (dump_layers == 0 && n->block_kernel == 3 && (!h_save || y_save))
+        return forward_bf16_zs(n, x, in_scale, in_scale_stride, out, B, L, w, st, h_save, y_save);
     REQUIRE(w.Bc == B, "internal: the pair-kernel path needs a whole-batch workspace (B=%d, pass=%d)", B, w.Bc);
     {
         ScopedTimer t(n, ADB_TIMER_AUX, st, 2);

@@ -7,6 +7,7 @@
 // derivative kernels, the bias / embedding reductions, the weight-norm chain rule and the fused AdamW update
 // (torch.optim.AdamW semantics, configs/model/diffunet_complex.yaml:7-12).
 #pragma once
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "cl_ops.cuh"
 
@@ -154,6 +155,26 @@ __global__ void permute_gate_cols_kernel(const float* __restrict__ in, const flo
 }
 
 // dst (bf16) = src (fp32)
+// fp16 -> bf16, 8 values per thread (the z stash of the forward is fp16; the weight-gradient GEMM takes bf16 operands)
+__global__ void __launch_bounds__(256) cvt_f16_bf16_kernel(const __nv_bfloat16* __restrict__ in_f16_bits, __nv_bfloat16* __restrict__ out,
+                                                           long long n) {
+    const long long n8 = n / 8;                                 // n % 8 == 0 and 16-byte aligned buffers at every call site
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint4 v = reinterpret_cast<const uint4*>(in_f16_bits)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
+            const float2 f = __half22float2(h);
+            const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+            o[k] = *reinterpret_cast<const uint32_t*>(&b);
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 __global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n,
                                                            float scale = 1.0f) {
     const long long n4 = n / 4;                                 // n % 4 == 0 and 16-byte aligned buffers at every call site

@@ -50,6 +50,8 @@ struct BlockZsParams {
     const float* b2;                // [512] output-projection bias of this layer (first 256 used here)
     const __nv_bfloat16* h_in;      // [B][L][256] (residual input, read by epilogue 2)
     __nv_bfloat16* h_out_dbg;       // ADB_DEBUG builds only: h' for the LSU-store timing experiment
+    __nv_bfloat16* y_out;           // training forward: pre-gate activations of this block, [B][L][512] bf16 as [gate 0..255 | filter
+                                    // 0..255] (what the backward's gate-derivative pass reads), or nullptr (sampling)
     int B, L, layer, layers, dil;
     int tiles_per_b, num_tiles;
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
@@ -331,6 +333,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                             const uint32_t tg = tanh_f16x2(pack_f16x2(g0, g1));
                             const uint32_t tf = tanh_f16x2(pack_f16x2(f0, f1));
                             zp[cc][i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
+                            if (p.y_out) { g[i >> 1] = pack_bf16x2(2.0f * g0, 2.0f * g1); f[i >> 1] = pack_bf16x2(f0, f1); }   // g0 = y_gate / 2
                         }
                     } else {
                         // boundary tile (~4 % of the tiles): per-row tap masks, constants straight from global memory
@@ -353,7 +356,19 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                             const uint32_t tg = tanh_f16x2(pack_f16x2(gv[0], gv[1]));
                             const uint32_t tf = tanh_f16x2(pack_f16x2(fv[0], fv[1]));
                             zp[cc][i >> 1] = hmul2(hfma2(tg, 0x38003800u, 0x38003800u), tf);
+                            if (p.y_out) { g[i >> 1] = pack_bf16x2(2.0f * gv[0], 2.0f * gv[1]); f[i >> 1] = pack_bf16x2(fv[0], fv[1]); }
                         }
+                    }
+                    if (p.y_out && tile_valid && t < p.L) {
+                        // training: keep y for the backward (64 contiguous bytes per half: two full-sector 256-bit stores each)
+                        __nv_bfloat16* yrow = p.y_out + (static_cast<long long>(b) * p.L + t) * 512 + c0;
+                        uint32_t lo[8], hi[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { lo[i] = g[i]; hi[i] = g[8 + i]; }
+                        stg256(yrow, lo); stg256(yrow + 16, hi);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { lo[i] = f[i]; hi[i] = f[8 + i]; }
+                        stg256(yrow + 256, lo); stg256(yrow + 256 + 16, hi);
                     }
                 }
                 // the accumulator is drained: hand it back before touching shared memory
