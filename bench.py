@@ -53,6 +53,31 @@ WORKLOAD = (f"DiffWave C={C} layers={LAYERS} cycle={CYCLE}, SC09 shape 1x{L}, ED
             f"evaluations), sigma_data={SIGMA_DATA}, Karras(0.002,80,rho=7), s_churn=0 (BASELINE.json configs[1])")
 
 
+class quiet_stdout:
+    """Route the process-level stdout (fd 1) to stderr while NCCL initialises: its version banner goes to stdout on some boxes and
+    the contract is ONE JSON line there."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def init_nccl(dev):
+    import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")            # keep stdout to the JSON line(s)
+    with quiet_stdout():
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)                                             # communicator (and its banner) created here
+        torch.cuda.synchronize(dev)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -222,8 +247,7 @@ def run_unet(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     B = args.batch or 128
     torch.manual_seed(0)
     net = UNet1dBase(precision=args.precision, **UNET_CFG4)
@@ -333,8 +357,7 @@ def run_train(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     B = args.batch or (32 if args.precision == "bf16" else 4)   # 32 = data.batch_size of the reference experiment (diffunet_complex_sc09.yaml:67)
     torch.manual_seed(0)                                   # identical initial weights on every rank, like DDP's broadcast
     net = WaveNetNoise(C, LAYERS, CYCLE, precision=args.precision)
@@ -493,8 +516,7 @@ def run_diffwave(args, rank, world, local_rank, batches):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # keep stdout to the JSON line(s)
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     torch.manual_seed(0)
     net = WaveNetNoise(C, LAYERS, CYCLE, precision=args.precision)      # the reference's own init scheme (wavenet.py:75, :30)
     # the reference zero-initialises the output conv (wavenet.py:57-66): re-randomise it so the trajectory is not trivial
