@@ -385,6 +385,9 @@ struct adb_wavenet {
     float* mtab = nullptr;            // [512][layers*3*512]  (W1[tap] Wp)^T
     float* cvec = nullptr;            // [layers*3*512]       W1[tap] bp (+ b1 for the centre tap)
     CUtensorMap tm_w, tm_w2, tm_w4, tm_wsp;     // weight maps with box rows 256 / 128 / 64 (cluster 1 / 2 / 4)
+    CUtensorMap tm_wsp2;                        // skip-projection weights with 128-row boxes (CTA-pair halves, fused skip GEMM + tail)
+    int fuse_tail = 1;                          // z-stash path: tail fused into the skip GEMM's epilogue when one GEMM covers all layers
+                                                // (ADB_FUSE_TAIL=0: separate skip GEMM + tail kernels)
     int cluster = 2;                            // CTAs per cluster for the single-CTA residual-block kernel (ADB_TC_CLUSTER)
     // Residual-block kernel of the bf16 sampling path, fixed when the handle is created (ADB_BLOCK_KERNEL):
     //   3 (default) z-stash kernel + skip GEMM (wavenet_tc3.cuh)   2 pair kernel with the fp16 skip stash (wavenet_tc2.cuh)
@@ -735,6 +738,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         if (!rc2) rc2 = make_weight_map(&n->tm_w2, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 128);
         if (!rc2) rc2 = make_weight_map(&n->tm_w4, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 64);
         if (!rc2) rc2 = make_weight_map(&n->tm_wsp, n->wsp_tc, 4 * 256);
+        if (!rc2) rc2 = make_weight_map(&n->tm_wsp2, n->wsp_tc, 4 * 256, 128);
         {
             const char* e = getenv("ADB_TC_CLUSTER");
             if (e) n->cluster = atoi(e);
@@ -746,6 +750,8 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             n->no_stash = n->block_kernel == 1;
             const char* pe = getenv("ADB_ZS_PIPE");
             if (pe) n->zs_pipe = atoi(pe) != 0;
+            const char* fe = getenv("ADB_FUSE_TAIL");
+            if (fe) n->fuse_tail = atoi(fe) != 0;
             const char* ce = getenv("ADB_CHUNK");
             if (ce && atoi(ce) > 0) n->chunk = atoi(ce);
             const char* se = getenv("ADB_STASH_GB");
@@ -762,6 +768,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_skip_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_GEMM_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_skip_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_TAIL_SMEM_BYTES));
     }
     rc = refold(n);
     if (rc) { adb_wavenet_destroy(n); return rc; }
@@ -923,6 +930,8 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
     const int C = n->C, layers = n->layers;
     const int num_sms = sm_count();
     const int tiles_per_b = (L + TC_TILE_T - 1) / TC_TILE_T;
+    // the training step needs the fp32 skip sum itself (tail backward), so it keeps the separate kernels
+    const bool fused_tail = n->fuse_tail && w.G == layers && !h_save;
     for (int b0 = 0; b0 < B; b0 += w.Bc) {
         const int bc = (B - b0 < w.Bc) ? B - b0 : w.Bc;
         const long long BL = static_cast<long long>(bc) * L;
@@ -976,7 +985,19 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
             }
             if (h_save) { hin = hout; hout = (l + 2 < layers) ? hin + BL * C : w.hbB; }
             else { __nv_bfloat16* tmp = hin; hin = hout; hout = tmp; }
-            if (slot == w.G - 1 || l + 1 == layers) {
+            if (fused_tail) {
+                if (l + 1 == layers) {
+                    // one GEMM over all layers with the tail in its epilogue: the fp32 skip sum never reaches HBM
+                    ScopedTimer t(n, ADB_TIMER_SKIP, st);
+                    SkipTailParams sp;
+                    sp.bias = n->skip_bias; sp.b_sp = n->b_sp; sp.w_out = n->w_out; sp.b_out = n->b_out;
+                    sp.out = out + static_cast<long long>(b0) * L;
+                    sp.scale = static_cast<float>(sqrt(1.0 / layers));
+                    sp.B = bc; sp.L = L; sp.tiles_per_b = tiles_per_b; sp.num_tiles = num_tiles; sp.G = layers;
+                    lc.dynamicSmemBytes = SKIP_TAIL_SMEM_BYTES;
+                    CK(cudaLaunchKernelEx(&lc, wavenet_skip_tail_kernel, m_zld, n->tm_w2, n->tm_wsp2, sp));
+                }
+            } else if (slot == w.G - 1 || l + 1 == layers) {
                 ScopedTimer t(n, ADB_TIMER_SKIP, st);
                 SkipGemmParams sp;
                 sp.G = slot + 1; sp.layer0 = l - slot;
@@ -987,7 +1008,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 CK(cudaLaunchKernelEx(&lc, wavenet_skip_gemm_kernel, m_zld, n->tm_w2, m_skip, sp));
             }
         }
-        {
+        if (!fused_tail) {
             ScopedTimer t(n, ADB_TIMER_TAIL, st);
             TailTcParams tp;
             tp.skip = w.skip; tp.b_sp = n->b_sp; tp.w_out = n->w_out; tp.b_out = n->b_out;

@@ -651,6 +651,239 @@ wavenet_skip_gemm_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skip GEMM with the network's tail fused into its epilogue (all `layers` blocks in one K loop):
+//   skip = bias + sum_l W2s_l z_l                                         (wavenet.py:114, :145-149)
+//   F[b][t] = b_out + sum_c w_out[c] relu(b_sp[c] + sum_k Wsp[c][k] skip[k] / sqrt(layers))   (wavenet.py:151, :177-179)
+// The fp32 skip sum never reaches HBM (the unfused pair of kernels writes and re-reads 4.2 GB per 256-sample evaluation).
+// Per tile group: job S (K = 256 * layers, accumulator 0) -> epilogue a: (acc + bias) * scale -> bf16 A operand in shared
+// memory -> job T (K = 256 against the skip-projection weights streamed through the same stage ring, accumulator 1) -> epilogue
+// b: relu, dot with w_out over the 256 columns (two warps per row quarter, halves combined through shared memory).
+// Job S of the next group only needs accumulator 0, which epilogue a has drained before job T starts.
+// ------------------------------------------------------------------------------------------------
+struct SkipTailSmem {
+    static constexpr int stages = 0;
+    static constexpr int a2 = SG_STAGES * T3_STAGE_BYTES;           // 4 K-blocks [128 t][64 ch] bf16, 128-byte swizzle (64 KB)
+    static constexpr int part = a2 + TC_Z_BYTES;                    // 128 fp32 partial row sums
+    static constexpr int bars = part + 512;
+    static constexpr int tmem_ptr = bars + 16 * 8;
+    static constexpr int total = tmem_ptr + 16;
+};
+static_assert(SkipTailSmem::a2 % 1024 == 0, "swizzle alignment");
+static_assert(SkipTailSmem::total <= 232448, "shared memory budget");
+constexpr int SKIP_TAIL_SMEM_BYTES = SkipTailSmem::total;
+
+struct SkipTailParams {
+    const float* bias;              // [256] sum over all layers of the skip half of b2
+    const float* b_sp;              // [256]
+    const float* w_out;             // [256]
+    const float* b_out;             // [1]
+    float* out;                     // [B][L]
+    float scale;                    // sqrt(1 / layers)
+    int B, L, tiles_per_b, num_tiles;
+    int G;                          // = layers
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wavenet_skip_tail_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w,
+                         const __grid_constant__ CUtensorMap tm_wsp, const SkipTailParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_part = reinterpret_cast<float*>(smem + SkipTailSmem::part);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SkipTailSmem::bars);
+    uint64_t* bar_full = bars;                   // [SG_STAGES] rank 0
+    uint64_t* bar_empty = bars + SG_STAGES;      // [SG_STAGES] per CTA
+    uint64_t* bar_tfull = bars + 2 * SG_STAGES;  // [2] per CTA: accumulator 0 (job S) / 1 (job T) ready
+    uint64_t* bar_tempty = bar_tfull + 2;        // [2] rank 0
+    uint64_t* bar_a2 = bar_tempty + 2;           // [1] rank 0: the A operand of job T is written
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SkipTailSmem::tmem_ptr);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_z);
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_wsp);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < SG_STAGES; ++s) { mbar_init(&bar_full[s], 2); mbar_init(&bar_empty[s], 1); }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_tfull[i], 1);
+                mbar_init(&bar_tempty[i], 2 * (TC_EPI_THREADS / 32));
+            }
+            mbar_init(bar_a2, 2 * (TC_EPI_THREADS / 32));
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair(s_tmem, 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+    constexpr uint32_t IDESC_F16 = umma_idesc_pair_f16(256);
+    constexpr uint32_t IDESC_BF16 = umma_idesc_pair_bf16(256);
+
+    const int pair_id = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_groups = (p.num_tiles + 1) >> 1;
+    const int nkb = 4 * p.G;
+
+    if (warp == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
+            const int tile = grp * 2 + rank;
+            const bool tile_valid = tile < p.num_tiles;
+            const int b = tile_valid ? tile / p.tiles_per_b : 0;     // a padding tile re-reads sample 0 (never stored)
+            const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
+            for (int kb = 0; kb < nkb + 4; ++kb) {
+                mbar_wait(&bar_empty[stage], phase ^ 1, SITE_PROD_EMPTY, stage);
+                if (lane == 0) {
+                    uint8_t* sa = smem + SkipTailSmem::stages + stage * T3_STAGE_BYTES;
+                    uint8_t* sb = sa + T3_A_BYTES;
+                    if (kb < nkb) {
+                        const int l = kb >> 2, cib = kb & 3;
+                        const int wblk = l * TC_W_BLOCKS_PER_LAYER + 28 + cib;
+                        if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * T3_STAGE_BYTES);
+                        else        mbar_arrive_cluster(&bar_full[stage], 0);
+                        tma_load_3d_pair(sa, &tm_z, &bar_full[stage], cib * 64, t0, l * p.B + b);
+                        tma_load_2d_pair(sb, &tm_w, &bar_full[stage], 0, wblk * 256 + rank * 128);
+                    } else {
+                        // job T: this CTA's half of K-block kb - nkb of the skip-projection weights
+                        if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * T3_B_BYTES);
+                        else        mbar_arrive_cluster(&bar_full[stage], 0);
+                        tma_load_2d_pair(sb, &tm_wsp, &bar_full[stage], 0, (kb - nkb) * 256 + rank * 128);
+                    }
+                }
+                __syncwarp();
+                if (++stage == SG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            const uint32_t a2_addr = smem_u32(smem + SkipTailSmem::a2);
+            for (int grp = pair_id; grp < num_groups; grp += num_pairs, ++it) {
+                // ---- job S -> accumulator 0 ----
+                mbar_wait(&bar_tempty[0], (it & 1) ^ 1, SITE_MMA_TEMPTY, 0);
+                tc_fence_after_sync();
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bar_full[stage], phase, SITE_MMA_FULL, stage);
+                    tc_fence_after_sync();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + SkipTailSmem::stages + stage * T3_STAGE_BYTES);
+                        const uint32_t sb = sa + T3_A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss_pair(tmem_base, umma_desc_sw128_kmajor(sa + k * 32), umma_desc_sw128_kmajor(sb + k * 32),
+                                              IDESC_F16, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair_mc(&bar_empty[stage], 3);
+                        if (kb == nkb - 1) umma_commit_pair_mc(&bar_tfull[0], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == SG_STAGES) { stage = 0; phase ^= 1; }
+                }
+                // ---- job T -> accumulator 1 (A = the scaled skip sum written by epilogue a) ----
+                mbar_wait(&bar_tempty[1], (it & 1) ^ 1, SITE_MMA_TEMPTY, 1);
+                mbar_wait(bar_a2, it & 1, SITE_MMA_ZREADY, 0);
+                tc_fence_after_sync();
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(&bar_full[stage], phase, SITE_MMA_FULL, stage);
+                    tc_fence_after_sync();
+                    if (lane == 0) {
+                        const uint32_t sb = smem_u32(smem + SkipTailSmem::stages + stage * T3_STAGE_BYTES) + T3_A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss_pair(tmem_base + 256, umma_desc_sw128_kmajor(a2_addr + kb * TC_A_BYTES + k * 32),
+                                              umma_desc_sw128_kmajor(sb + k * 32), IDESC_BF16, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair_mc(&bar_empty[stage], 3);
+                        if (kb == 3) umma_commit_pair_mc(&bar_tfull[1], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == SG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* a2 = smem + SkipTailSmem::a2;
+        const float b_out = __ldg(p.b_out);
+        uint32_t it = 0;
+        for (int grp = pair_id; grp < num_groups; grp += num_pairs, ++it) {
+            const int tile = grp * 2 + rank;
+            const bool tile_valid = tile < p.num_tiles;
+            const int b = tile / p.tiles_per_b;
+            const int t = (tile % p.tiles_per_b) * TC_TILE_T + row;
+            // ---- epilogue a: (skip + bias) / sqrt(layers) -> bf16 A operand of the skip projection ----
+            mbar_wait(&bar_tfull[0], it & 1, SITE_EPI_TFULL, 0);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col = half * 128 + cc * 32;
+                uint32_t r[32];
+                tmem_ld_32x32(t_lane + col, r);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                    pk[i >> 1] = pack_bf16x2((__uint_as_float(r[i]) + __ldg(p.bias + col + i)) * p.scale,
+                                             (__uint_as_float(r[i + 1]) + __ldg(p.bias + col + i + 1)) * p.scale);
+                uint8_t* arow = a2 + (col >> 6) * TC_A_BYTES + row * 128;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int chunk = (((col & 63) >> 3) + m) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(arow + chunk * 16) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cluster(&bar_tempty[0], 0);
+                mbar_arrive_cluster(bar_a2, 0);
+            }
+            // ---- epilogue b: F = b_out + sum_c w_out[c] relu(s2[c] + b_sp[c]) ----
+            mbar_wait(&bar_tfull[1], it & 1, SITE_EPI_TFULL, 1);
+            tc_fence_after_sync();
+            float acc = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col = half * 128 + cc * 32;
+                uint32_t r[32];
+                tmem_ld_32x32(t_lane + 256 + col, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    acc = fmaf(fmaxf(__uint_as_float(r[i]) + __ldg(p.b_sp + col + i), 0.f), __ldg(p.w_out + col + i), acc);
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bar_tempty[1], 0);
+            named_bar_sync(1, TC_EPI_THREADS);                   // the previous group's partial sums have been consumed
+            if (half == 1) s_part[row] = acc;
+            named_bar_sync(1, TC_EPI_THREADS);
+            if (half == 0 && tile_valid && t < p.L) p.out[static_cast<long long>(b) * p.L + t] = acc + s_part[row] + b_out;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
 // bias[n] = sum_l b2_l[256 + n]  (the skip half of every block's output-projection bias, wavenet.py:114)
 __global__ void skip_bias_sum_kernel(const float* const* __restrict__ b2_tab, int layers, float* __restrict__ out) {
     const int n = threadIdx.x;
