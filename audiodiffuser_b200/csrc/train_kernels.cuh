@@ -283,51 +283,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, f
     for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(o + c, red[c]);
 }
 
-// Per-sample column sums of dy over three row ranges at once: out[0] all rows, out[1] rows t < d, out[2] rows t >= L - d
-// (out: [3][nb][C] fp32, zeroed by the caller). They turn the step-embedding term of the dilated conv's weight gradient into a
-// rank-B correction (see wgrad_pcorr_kernel), so (h + p) never has to be materialised for the backward.
-template <typename T>
-__global__ void __launch_bounds__(256) colsum3_kernel(const T* __restrict__ in, float* __restrict__ out, int L, int C, int chunks,
-                                                      int d, int nb) {
-    constexpr int VE = ClVec<T>::N;
-    const int b = blockIdx.y, chunk = blockIdx.x;
-    const int rows_per = (L + chunks - 1) / chunks;
-    const int r0 = chunk * rows_per, r1 = min(L, r0 + rows_per);
-    __shared__ float red[3][1024];
-    for (int c = threadIdx.x; c < 3 * 1024; c += blockDim.x) (&red[0][0])[c] = 0.f;
-    __syncthreads();
-    const int vpr = C / VE;
-    const int rstep = 256 / vpr, rofs = threadIdx.x / vpr, v = threadIdx.x % vpr;
-    float s[3][VE];
-#pragma unroll
-    for (int k = 0; k < VE; ++k) s[0][k] = s[1][k] = s[2][k] = 0.f;
-    const T* col = in + static_cast<size_t>(b) * L * C + v * VE;
-    for (int r = r0 + rofs; r < r1; r += rstep) {
-        float x[VE];
-        ClVec<T>::load(col + static_cast<size_t>(r) * C, x);
-        const float lo = r < d ? 1.f : 0.f, hi = r >= L - d ? 1.f : 0.f;
-#pragma unroll
-        for (int k = 0; k < VE; ++k) { s[0][k] += x[k]; s[1][k] = fmaf(lo, x[k], s[1][k]); s[2][k] = fmaf(hi, x[k], s[2][k]); }
-    }
-    const bool any_lo = r0 < d, any_hi = r1 > L - d;
-#pragma unroll
-    for (int k = 0; k < VE; ++k) {
-        atomicAdd(&red[0][v * VE + k], s[0][k]);
-        if (any_lo) atomicAdd(&red[1][v * VE + k], s[1][k]);
-        if (any_hi) atomicAdd(&red[2][v * VE + k], s[2][k]);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(out + (static_cast<size_t>(0) * nb + b) * C + c, red[0][c]);
-        if (any_lo) atomicAdd(out + (static_cast<size_t>(1) * nb + b) * C + c, red[1][c]);
-        if (any_hi) atomicAdd(out + (static_cast<size_t>(2) * nb + b) * C + c, red[2][c]);
-    }
-}
-
 // Step-embedding term of the dilated conv's weight gradient (wavenet.py:108-110): the conv sees x = h + p_b inside [0, L) and
 // zeros outside, so  dW1[tap][i][j] = sum_b sum_t h_b[t + s_tap][i] dy_b[t][j]  +  sum_b p_b[i] * (sum over the rows t whose
 // tap stays inside the sample of dy_b[t][j]).  The first term is the tensor-core GEMM on h itself; this kernel adds the second
-// from the three per-sample column sums S (all rows / first d rows / last d rows) and also writes db1[j] = sum_b S_all[b][j].
+// from the three per-sample column sums S (all rows / first d rows / last d rows — a by-product of the weight-gradient GEMM, see
+// WgradTcParams::colsum_mode) and also writes db1[j] = sum_b S_all[b][j].
 //   tap 0 (t - d >= 0): S_all - S_lo ;  tap 1: S_all ;  tap 2 (t + d < L): S_all - S_hi.   gw1: [3][C][N] fp32, N = 2C.
 __global__ void __launch_bounds__(256) wgrad_pcorr_kernel(const float* __restrict__ p /*[B][C]*/, const float* __restrict__ S /*[3][B][N]*/,
                                                           float* __restrict__ gw1, float* __restrict__ db1, int B, int C, int N) {

@@ -39,6 +39,12 @@ struct WgradTcParams {
     int splits;             // CTAs sharing one tile
     int chunks_per_b;       // ceil(L / 64)
     float scale;            // multiplies the result (e.g. the skip-sum scale of wavenet.py:151)
+    // Column sums of G as a by-product (the CTAs of the first m-tile and the unshifted tap already stage every G tile of their K
+    // slab; their four epilogue warps, idle during the main loop, add the rows up from shared memory):
+    //   colsum_mode 1: colsum_out[b][n] += sum_t G[b][t][n]  for the first n-tile only (per-sample sums of the first 256 columns)
+    //   colsum_mode 2: colsum_out[k][b][n] += sums over all rows (k = 0), rows t < colsum_d (k = 1), rows t >= L - colsum_d (k = 2)
+    float* colsum_out;
+    int colsum_mode, colsum_d;
 };
 
 // MN-major SWIZZLE_128B shared-memory descriptor: 64-element (128-byte) rows along M/N, K advances one row per element;
@@ -67,10 +73,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    const int job = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+    const int tn = job % p.tiles_n, tm = (job / p.tiles_n) % p.tiles_m, tap = job / (p.tiles_n * p.tiles_m);
+    // every CTA of an n-tile stages the same G tiles (whatever its m-tile and tap): they share the column sums, CTA (tm, tap) taking
+    // every sum_ways-th chunk of the K slab, so that the adds stay far below the MMA time of a stage
+    const bool do_sum = p.colsum_mode != 0 && (p.colsum_mode == 2 || tn == 0);
+    const int sum_ways = p.tiles_m * p.taps, sum_me = tm * p.taps + tap;
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_g); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+            // a stage is free once its MMAs have completed AND (column-sum CTAs) the four epilogue warps have read its G tile
+            for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], do_sum ? 5 : 1); }
             mbar_init(bar_done, 1);
             fence_mbar_init();
         }
@@ -83,8 +96,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
 
-    const int job = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
-    const int tn = job % p.tiles_n, tm = (job / p.tiles_n) % p.tiles_m, tap = job / (p.tiles_n * p.tiles_m);
     const int shift = (tap - p.taps / 2) * p.dil;
     const int m0 = tm * 128, n0 = tn * 256;
     const int total_chunks = p.B * p.chunks_per_b;
@@ -126,6 +137,72 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (my_chunks > 0) {
+        if (do_sum) {
+            // ---- column sums of G, straight from the staged boxes: warp w owns box w (64 channels); a lane reads 16 bytes (8
+            //      channels) of a row, 8 lanes cover a 128-byte row and the warp 4 rows per instruction (conflict-free). Lanes
+            //      l, l + 8, l + 16, l + 24 hold partial sums of the same channels and are combined when a sample ends ----
+            const int w = warp - 2;
+            const int cch = lane & 7, rsub = lane >> 3;          // 16-byte chunk of the row / row within a group of 4
+            uint32_t stage = 0, phase = 0;
+            float acc[3][8];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+            int cur_b = -1;
+            auto flush = [&]() {
+                if (cur_b >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (p.colsum_mode == 1 && k > 0) break;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float v = acc[k][e];
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            if (rsub == 0 && v != 0.f) {
+                                const int n = n0 + 64 * w + 8 * cch + e;
+                                float* o = p.colsum_mode == 1 ? p.colsum_out + static_cast<long long>(cur_b) * 256 + n
+                                                              : p.colsum_out + (static_cast<long long>(k) * p.B + cur_b) * p.Cg + n;
+                                atomicAdd(o, v);
+                            }
+                            acc[k][e] = 0.f;
+                        }
+                    }
+                }
+            };
+            for (int i = 0; i < my_chunks; ++i) {
+                const int chunk = split + i * p.splits;
+                const int b = chunk / p.chunks_per_b, t0 = (chunk % p.chunks_per_b) * WG_KT;
+                mbar_wait(&bar_full[stage], phase, SITE_WG_FULL, stage);       // also orders this arrival after the previous use of the stage
+                if (i % sum_ways == sum_me) {
+                    if (b != cur_b) { flush(); cur_b = b; }
+                    const uint8_t* box = smem + stage * WG_STAGE_BYTES + WG_A_BYTES + w * WG_BOX_BYTES;
+                    const bool edge = p.colsum_mode == 2 && (t0 < p.colsum_d || t0 + WG_KT > p.L - p.colsum_d);
+#pragma unroll 4
+                    for (int r4 = 0; r4 < WG_KT; r4 += 4) {
+                        const int r = r4 + rsub;
+                        const uint4 v = *reinterpret_cast<const uint4*>(box + r * 128 + ((cch ^ (r & 7)) << 4));
+                        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+                        float x[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { x[2 * e] = bf16_lo(u[e]); x[2 * e + 1] = bf16_hi(u[e]); }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[0][e] += x[e];
+                        if (edge) {
+                            const int t = t0 + r;
+                            const float lo = t < p.colsum_d ? 1.f : 0.f, hi = t >= p.L - p.colsum_d ? 1.f : 0.f;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { acc[1][e] = fmaf(lo, x[e], acc[1][e]); acc[2][e] = fmaf(hi, x[e], acc[2][e]); }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[stage]);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+            flush();
+        }
         const int q = warp & 3;
         const int row = q * 32 + lane;                     // output row within the tile = input channel m0 + row
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
