@@ -400,6 +400,7 @@ struct adb_wavenet {
     int chunk = 256;                            // samples per pass of the bf16 stack (ADB_CHUNK): bounds the workspace
     int64_t stash_budget = 80LL << 30;          // bytes the z stash may take (ADB_STASH_GB); fewer layers per skip GEMM if it does not fit
     int dbg = 0;                                // ADB_DEBUG builds: ADB_DEBUG_FLAGS at create (2 = in-kernel cycle accounting)
+    RefoldLayer* d_refold = nullptr;            // per-block pointer table of refold_layers_kernel
     float* skip_bias = nullptr;                 // [256] sum over layers of the skip half of b2
     const float** d_b2 = nullptr;               // per-layer b2 pointers (device)
     std::vector<HMap> hmaps;
@@ -549,28 +550,12 @@ static int refold(adb_wavenet* n) {
     scale_copy_kernel<<<1, 256>>>(n->v_in, n->d_scale + 0, n->w_in_f, C);
     pack_conv_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->v_sp, n->d_scale + njobs - 1, n->wsp_f, C, C, 1);
     transpose_f32_kernel<<<grid_for(static_cast<long long>(C) * C), 256>>>(n->wsp_f, n->wspT, C, C);
-    for (int l = 0; l < layers; ++l) {
-        LayerW& w = n->L[l];
-        pack_conv_f32_kernel<<<grid_for(6LL * C * C), 256>>>(w.v1, n->d_scale + 1 + 2 * l, w.w1f, 2 * C, C, 3);
-        pack_conv_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.v2, n->d_scale + 2 + 2 * l, w.w2f, 2 * C, C, 1);
-        transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2f, w.w2T, C, 2 * C);                 // [ci][co] -> [co][ci]
-        for (int tap = 0; tap < 3; ++tap)                                                              // tap-reversed transpose
-            transpose_f32_kernel<<<grid_for(2LL * C * C), 256>>>(w.w1f + static_cast<size_t>(2 - tap) * C * 2 * C,
-                                                                 w.w1d + static_cast<size_t>(tap) * 2 * C * C, C, 2 * C);
-    }
+    // every block's folded / transposed / packed weights in ONE launch (13 launches per block before)
+    refold_layers_kernel<<<dim3(148 * 2, layers), 256>>>(n->d_refold, C);
     CK(cudaGetLastError());
     n->tc_ready = false;
     if (C == TC_C) {
         const long long ldm = static_cast<long long>(layers) * 1536;
-        for (int l = 0; l < layers; ++l) {
-            LayerW& w = n->L[l];
-            pack_tc_layer_kernel<<<148 * 4, 256>>>(w.w1f, w.w2f, n->wtc + static_cast<size_t>(l) * 32 * 256 * 64);
-            permute_gate_cols_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1f, w.b1, n->w1perm, w.b1p, 3 * C, C);
-            cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(n->w1perm, w.w1p, C, 2 * C, 3);
-            cl_pack_conv_tc_kernel<<<grid_for(2LL * C * C), 256>>>(w.w2T, w.w2Tp, 2 * C, C, 1);
-            cl_pack_conv_tc_kernel<<<grid_for(6LL * C * C), 256>>>(w.w1d, w.w1dp, 2 * C, C, 3);
-            transpose_f32_kernel<<<grid_for(512LL * C), 256>>>(w.wp, n->wpT + static_cast<size_t>(l) * 512 * C, C, 512);   // [C][512] -> [512][C]
-        }
         {
             // Step-embedding fold tables for all layers and taps in two launches (operands through pointer tables):
             //   mtab[k][l,tap,co] = sum_ci Wp_l[ci][k] * W1_l[tap][ci][co]
@@ -769,6 +754,23 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_skip_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_GEMM_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_skip_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_TAIL_SMEM_BYTES));
+    }
+    {
+        // per-block pointer table of refold_layers_kernel
+        std::vector<RefoldLayer> tab(layers);
+        for (int l = 0; l < layers; ++l) {
+            const LayerW& w = n->L[l];
+            RefoldLayer& r = tab[l];
+            r.v1 = w.v1; r.v2 = w.v2; r.wp = w.wp; r.b1 = w.b1;
+            r.s1 = n->d_scale + 1 + 2 * l; r.s2 = n->d_scale + 2 + 2 * l;
+            r.w1f = w.w1f; r.w2f = w.w2f; r.w2T = w.w2T; r.w1d = w.w1d;
+            r.wpT = n->wpT + static_cast<size_t>(l) * 512 * C;
+            r.b1p = w.b1p;
+            r.wtc = n->wtc ? n->wtc + static_cast<size_t>(l) * 32 * 256 * 64 : nullptr;
+            r.w1p = w.w1p; r.w2Tp = w.w2Tp; r.w1dp = w.w1dp;
+        }
+        CKN(dmalloc(n, &n->d_refold, layers));
+        CKN(cudaMemcpy(n->d_refold, tab.data(), sizeof(RefoldLayer) * layers, cudaMemcpyHostToDevice));
     }
     rc = refold(n);
     if (rc) { adb_wavenet_destroy(n); return rc; }

@@ -154,6 +154,100 @@ __global__ void permute_gate_cols_kernel(const float* __restrict__ in, const flo
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Everything a residual block derives from its parameters, for ALL blocks in one launch (grid.y = block). Every derived
+// element is one scaled gather from the weight-normed tensors v1 [2C][C][3], v2 [2C][C] (scale = g / ||v||), the embedding
+// projection wp [C][512] or the conv bias b1 [2C]; an optimizer step used to issue 13 small launches per block for this:
+//   w1f [3][C][2C] fp32   folded dilated-conv weights (ci-major)            w2f [C][2C] fp32   folded 1x1 weights
+//   w2T [2C][C]           = w2f transposed (dz = DO W2^T)                   w1d [3][2C][C]     tap-reversed transpose (dx)
+//   wpT [512][C]          transposed embedding projection (fold tables)
+//   wtc [32][256][64]     TMA blocks of the forward kernels (G1 bf16, G2 fp16; wavenet_tc.cuh pack order)
+//   w1p / w2Tp / w1dp     the same three matrices as cl_conv_tc blocks [kb][N][64] bf16 (w1p with the [128 gate | 128 filter]
+//                         column order of CL_MODE_GATE_FWD), b1p the conv bias in that column order
+// ------------------------------------------------------------------------------------------------
+struct RefoldLayer {
+    const float *v1, *v2, *wp, *b1, *s1, *s2;
+    float *w1f, *w2f, *w2T, *w1d, *wpT, *b1p;
+    __nv_bfloat16 *wtc, *w1p, *w2Tp, *w1dp;
+};
+
+__device__ __forceinline__ int gate_perm_src(int np, int C) {      // column np of the permuted layout <- original column
+    const int j = np >> 8, r = np & 255;
+    return r < 128 ? 128 * j + r : C + 128 * j + (r - 128);
+}
+
+__global__ void __launch_bounds__(256) refold_layers_kernel(const RefoldLayer* __restrict__ tab, int C) {
+    const RefoldLayer L = tab[blockIdx.y];
+    const float s1 = L.s1[0], s2 = L.s2[0];
+    const long long N2 = 2LL * C, n_w1 = 3LL * C * N2, n_w2 = static_cast<long long>(C) * N2, n_wp = 512LL * C;
+    const bool tc = L.wtc != nullptr;                      // C == 256
+    const long long seg[10] = {n_w1, n_w2, n_w2, n_w1, n_wp, tc ? 32LL * 256 * 64 : 0, tc ? n_w1 : 0, tc ? n_w2 : 0, tc ? n_w1 : 0,
+                               tc ? N2 : 0};
+    long long total = 0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) total += seg[k];
+    for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
+         g += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long i = g;
+        int k = 0;
+        while (i >= seg[k]) { i -= seg[k]; ++k; }
+        switch (k) {
+            case 0: {   // w1f[tap][ci][co]
+                const int co = static_cast<int>(i % N2), ci = static_cast<int>((i / N2) % C), tap = static_cast<int>(i / (N2 * C));
+                L.w1f[i] = L.v1[(static_cast<long long>(co) * C + ci) * 3 + tap] * s1;
+                break;
+            }
+            case 1: {   // w2f[ci][co]
+                const int co = static_cast<int>(i % N2), ci = static_cast<int>(i / N2);
+                L.w2f[i] = L.v2[static_cast<long long>(co) * C + ci] * s2;
+                break;
+            }
+            case 2: L.w2T[i] = L.v2[i] * s2; break;          // w2T[co][ci] = w2f[ci][co]
+            case 3: {   // w1d[tap][co][ci] = w1f[2 - tap][ci][co]
+                const int ci = static_cast<int>(i % C), co = static_cast<int>((i / C) % N2), tap = static_cast<int>(i / (N2 * C));
+                L.w1d[i] = L.v1[(static_cast<long long>(co) * C + ci) * 3 + (2 - tap)] * s1;
+                break;
+            }
+            case 4: {   // wpT[k][c] = wp[c][k]
+                const int c = static_cast<int>(i % C), kk = static_cast<int>(i / C);
+                L.wpT[i] = L.wp[static_cast<long long>(c) * 512 + kk];
+                break;
+            }
+            case 5: {   // forward TMA blocks (pack_tc_layer_kernel order)
+                const int kk = static_cast<int>(i & 63), n = static_cast<int>((i >> 6) & 255), blk = static_cast<int>(i >> 14);
+                if (blk < 24) {
+                    const int j = blk / 12, kb = blk % 12, tap = kb >> 2, cib = kb & 3;
+                    const int co = n < 128 ? 128 * j + n : 256 + 128 * j + (n - 128);
+                    L.wtc[i] = __float2bfloat16_rn(L.v1[(static_cast<long long>(co) * C + cib * 64 + kk) * 3 + tap] * s1);
+                } else {
+                    const int j = (blk - 24) >> 2, kb = (blk - 24) & 3;
+                    const __half hv = __float2half_rn(L.v2[static_cast<long long>(256 * j + n) * C + kb * 64 + kk] * s2);
+                    L.wtc[i] = *reinterpret_cast<const __nv_bfloat16*>(&hv);      // GEMM2 runs in fp16: store the fp16 bit pattern
+                }
+                break;
+            }
+            case 6: {   // w1p: cl_conv_tc blocks of the column-permuted w1f (Cin = C, N = 2C, 3 taps)
+                const int kk = static_cast<int>(i & 63), n = static_cast<int>((i >> 6) % N2), kb = static_cast<int>(i / (64 * N2));
+                const int kbt = C / 64, tap = kb / kbt, ci = (kb % kbt) * 64 + kk;
+                L.w1p[i] = __float2bfloat16_rn(L.v1[(static_cast<long long>(gate_perm_src(n, C)) * C + ci) * 3 + tap] * s1);
+                break;
+            }
+            case 7: {   // w2Tp: blocks of w2T (Cin = 2C, N = C, 1 tap)
+                const int kk = static_cast<int>(i & 63), n = static_cast<int>((i >> 6) % C), kb = static_cast<int>(i / (64LL * C));
+                L.w2Tp[i] = __float2bfloat16_rn(L.v2[static_cast<long long>(kb * 64 + kk) * C + n] * s2);
+                break;
+            }
+            case 8: {   // w1dp: blocks of w1d (Cin = 2C, N = C, 3 taps)
+                const int kk = static_cast<int>(i & 63), n = static_cast<int>((i >> 6) % C), kb = static_cast<int>(i / (64LL * C));
+                const int kbt = static_cast<int>(N2 / 64), tap = kb / kbt, co = (kb % kbt) * 64 + kk;
+                L.w1dp[i] = __float2bfloat16_rn(L.v1[(static_cast<long long>(co) * C + n) * 3 + (2 - tap)] * s1);
+                break;
+            }
+            default: L.b1p[i] = L.b1[gate_perm_src(static_cast<int>(i), C)]; break;
+        }
+    }
+}
+
 // dst (bf16) = src (fp32)
 // fp16 -> bf16, 8 values per thread (the z stash of the forward is fp16; the weight-gradient GEMM takes bf16 operands)
 __global__ void __launch_bounds__(256) cvt_f16_bf16_kernel(const __nv_bfloat16* __restrict__ in_f16_bits, __nv_bfloat16* __restrict__ out,
@@ -289,22 +383,29 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, f
 // from the three per-sample column sums S (all rows / first d rows / last d rows — a by-product of the weight-gradient GEMM, see
 // WgradTcParams::colsum_mode) and also writes db1[j] = sum_b S_all[b][j].
 //   tap 0 (t - d >= 0): S_all - S_lo ;  tap 1: S_all ;  tap 2 (t + d < L): S_all - S_hi.   gw1: [3][C][N] fp32, N = 2C.
+// grid (N / 256, C / 8, 3 taps), 256 threads: a thread owns one column j and eight rows i; p of the block's rows sits in shared memory.
 __global__ void __launch_bounds__(256) wgrad_pcorr_kernel(const float* __restrict__ p /*[B][C]*/, const float* __restrict__ S /*[3][B][N]*/,
                                                           float* __restrict__ gw1, float* __restrict__ db1, int B, int C, int N) {
-    const long long total = 3LL * C * N;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int j = static_cast<int>(idx % N), i = static_cast<int>((idx / N) % C), tap = static_cast<int>(idx / (static_cast<long long>(N) * C));
-        float acc = 0.f, tot = 0.f;
-        for (int b = 0; b < B; ++b) {
-            const float sa = S[(static_cast<long long>(0) * B + b) * N + j];
-            const float sv = tap == 1 ? sa : sa - S[(static_cast<long long>(tap == 0 ? 1 : 2) * B + b) * N + j];
-            acc = fmaf(p[static_cast<long long>(b) * C + i], sv, acc);
+    __shared__ float ps[64 * 8];                              // [b][8 rows], B <= 64 per pass
+    const int j = blockIdx.x * 256 + threadIdx.x, i0 = blockIdx.y * 8, tap = blockIdx.z;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float tot = 0.f;
+    for (int b0 = 0; b0 < B; b0 += 64) {
+        const int nb = min(64, B - b0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb * 8; e += 256) ps[e] = p[static_cast<long long>(b0 + (e >> 3)) * C + i0 + (e & 7)];
+        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            const float sa = S[(static_cast<long long>(0) * B + b0 + b) * N + j];
+            const float sv = tap == 1 ? sa : sa - S[(static_cast<long long>(tap == 0 ? 1 : 2) * B + b0 + b) * N + j];
             tot += sa;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[r] = fmaf(ps[b * 8 + r], sv, acc[r]);
         }
-        gw1[idx] += acc;
-        if (tap == 1 && i == 0) db1[j] = tot;
     }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) gw1[(static_cast<long long>(tap) * C + i0 + r) * N + j] += acc[r];
+    if (tap == 1 && blockIdx.y == 0) db1[j] = tot;
 }
 
 // ------------------------------------------------------------------------------------------------
