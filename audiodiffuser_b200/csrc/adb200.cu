@@ -87,6 +87,21 @@ extern "C" int adb_debug_tc_cycles(unsigned long long* out16, int reset) {
     return ADB_OK;
 }
 
+// host view of the z-stash kernel's job order (wavenet_tc3.cuh: zs_job_at), for the CPU tests of the schedule: writes up to `cap`
+// (type, group) pairs and returns how many jobs the sequence has
+extern "C" int adb_debug_zs_job_order(int n_groups, int write_h, int pipelined, int* types, int* groups, int cap) {
+    const int slots = pipelined ? zs_num_slots<true>(n_groups, write_h) : zs_num_slots<false>(n_groups, write_h);
+    int count = 0;
+    for (int s = 0; s < slots; ++s) {
+        int type = 0, gi = 0;
+        const bool ok = pipelined ? zs_job_at<true>(s, n_groups, write_h, type, gi) : zs_job_at<false>(s, n_groups, write_h, type, gi);
+        if (!ok) continue;
+        if (count < cap && types && groups) { types[count] = type; groups[count] = gi; }
+        ++count;
+    }
+    return count;
+}
+
 extern "C" int adb_check_async(void) {
     CK(cudaDeviceSynchronize());
     SpinGuardState st;
@@ -375,7 +390,6 @@ struct adb_wavenet {
     __nv_bfloat16* wsp_p = nullptr;   // skip projection [C -> C] in cl_conv_tc blocks (training tail on the tensor cores)
     __nv_bfloat16* wspT_p = nullptr;  // its transpose (dskip = ds2 Wsp)
     const float** fold_tab = nullptr; // 6 x (layers*3) operand pointers of the two batched fold GEMMs (refold)
-    float* w1perm = nullptr;          // [3][C][2C] scratch of refold (column-permuted W1)
     std::vector<int64_t> counts, dst_off;   // flat-vector pieces (state_dict order) and their offsets in `params`
     const float** d_wp = nullptr;     // device arrays of per-layer pointers
     const float** d_bp = nullptr;
@@ -666,7 +680,6 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     CKN(dmalloc(n, &n->wsp_f, static_cast<size_t>(C) * C));
     CKN(dmalloc(n, &n->wspT, static_cast<size_t>(C) * C));
     CKN(dmalloc(n, &n->wpT, static_cast<size_t>(layers) * 512 * C));
-    CKN(dmalloc(n, &n->w1perm, 3ULL * C * 2 * C));
     std::vector<const float*> h_wp(layers), h_bp(layers);
     for (int l = 0; l < layers; ++l) {
         LayerW& w = n->L[l];

@@ -138,21 +138,6 @@ __global__ void __launch_bounds__(256) axpby_kernel(const T* __restrict__ x, flo
     }
 }
 
-// Column permutation for CL_MODE_GATE_FWD: column n' of every 256-wide tile j holds gate channel 128 j + r (r = n' % 256 < 128)
-// or filter channel 128 j + r - 128; out[row][n'] = in[row][perm(n')], bias likewise. in: [rows][2C].
-__global__ void permute_gate_cols_kernel(const float* __restrict__ in, const float* __restrict__ bias_in, float* __restrict__ out,
-                                         float* __restrict__ bias_out, int rows, int C) {
-    const long long total = static_cast<long long>(rows) * 2 * C;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int np = static_cast<int>(i % (2 * C));
-        const long long row = i / (2 * C);
-        const int j = np >> 8, r = np & 255;
-        const int nsrc = r < 128 ? 128 * j + r : C + 128 * j + (r - 128);
-        out[i] = in[row * 2 * C + nsrc];
-        if (row == 0) bias_out[np] = bias_in[nsrc];
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Everything a residual block derives from its parameters, for ALL blocks in one launch (grid.y = block). Every derived

@@ -631,34 +631,11 @@ wavenet_tail_tc_kernel(const __grid_constant__ CUtensorMap tm_wsp, const TailTcP
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight packing for the tensor-core path (run once when weights are loaded).
+// Weight packing for the tensor-core path. The per-block TMA blocks are written by refold_layers_kernel (train_kernels.cuh):
 //   GEMM1 blocks (job j in {0,1}, kb = tap * 4 + cib): row n < 128 -> gate channel 128 j + n,
 //   row n >= 128 -> filter channel 256 + 128 j + (n - 128)   (gate = FIRST half, wavenet.py:111)
-//   GEMM2 blocks (job j, kb): row n -> output row 256 j + n (j = 0 residual, 1 skip, wavenet.py:114)
-// Sources are the folded fp32 weights w1f [3][256][512] and w2f [256][512] (ci-major, co contiguous).
+//   GEMM2 blocks (job j, kb): row n -> output row 256 j + n (j = 0 residual, 1 skip, wavenet.py:114), fp16 bit patterns
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_tc_layer_kernel(const float* __restrict__ w1f, const float* __restrict__ w2f,
-                                     __nv_bfloat16* __restrict__ out /* [32][256][64] */) {
-    const int total = 32 * 256 * 64;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int k = i & 63, n = (i >> 6) & 255, blk = i >> 14;
-        float v;
-        if (blk < 24) {
-            const int j = blk / 12, kb = blk % 12, tap = kb >> 2, cib = kb & 3;
-            const int co = n < 128 ? 128 * j + n : 256 + 128 * j + (n - 128);
-            v = w1f[(static_cast<long long>(tap) * 256 + cib * 64 + k) * 512 + co];
-        } else {
-            const int j = (blk - 24) >> 2, kb = (blk - 24) & 3;
-            v = w2f[static_cast<long long>(kb * 64 + k) * 512 + 256 * j + n];
-            // GEMM2 runs in fp16 (z is fp16): store the bit pattern of the fp16 value in the 16-bit slot
-            const __half hv = __float2half_rn(v);
-            out[i] = *reinterpret_cast<const __nv_bfloat16*>(&hv);
-            continue;
-        }
-        out[i] = __float2bfloat16_rn(v);
-    }
-}
-
 // skip projection: out[kb][n][k] = wspf[kb*64 + k][n]
 __global__ void pack_tc_tail_kernel(const float* __restrict__ wspf, __nv_bfloat16* __restrict__ out) {
     const int total = 4 * 256 * 64;

@@ -69,12 +69,12 @@ struct BlockZsParams {
 // bubble. The producer, the MMA issuer and the epilogue warps all walk this sequence; slot s of the pipelined order that
 // has no job (i + 1 == n) returns false.
 template <bool PIPE>
-__device__ __forceinline__ int zs_num_slots(int n, int write_h) {
+__host__ __device__ __forceinline__ int zs_num_slots(int n, int write_h) {
     if (!write_h) return 2 * n;
     return PIPE ? 2 + 3 * n : 3 * n;
 }
 template <bool PIPE>
-__device__ __forceinline__ bool zs_job_at(int s, int n, int write_h, int& type, int& i) {
+__host__ __device__ __forceinline__ bool zs_job_at(int s, int n, int write_h, int& type, int& i) {
     if (!write_h) { i = s >> 1; type = s & 1; return true; }
     if (!PIPE) { i = s / 3; type = s - 3 * i; return true; }
     if (s < 2) { i = 0; type = s; return true; }

@@ -35,6 +35,10 @@ const char* adb_last_error(void);
 int adb_version(void);
 /* 0 if `device` is sm_100 (B200) and usable. */
 int adb_device_check(int device);
+/* Host view of the z-stash residual-block kernel's job order (types 0 = G1a, 1 = G1b, 2 = G2r; wavenet_tc3.cuh): fills up to `cap`
+ * (type, group) pairs and returns the number of jobs. No GPU involved; used by the CPU tests of the software-pipelined schedule. */
+int adb_debug_zs_job_order(int n_groups, int write_h, int pipelined, int* types, int* groups, int cap);
+
 /* Synchronise the device and report any asynchronous kernel / pipeline error (test & bench use). */
 int adb_check_async(void);
 /* Kernel launches issued so far by the op-level entry points (adb_edm_*, adb_cl_*, training step) on this process;

@@ -190,3 +190,38 @@ def test_philox_oracle_known_answers():
     assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 0.02 and abs((z ** 4).mean() - 3) < 0.1
     assert not np.array_equal(z[:16], churn_normals(77, 4, 5, 16)) and not np.array_equal(z[:16], churn_normals(77, 3, 6, 16))
     assert np.array_equal(z[:1001].astype(np.float32), churn_normals(77, 3, 5, 1001))         # ragged length: same stream, truncated
+
+
+def test_zstash_kernel_job_order():
+    """The job sequence every warp role of wavenet_block_zs_kernel walks (zs_job_at, exported for the host): each tile group gets
+    exactly one G1a, G1b and (unless the residual output is unused) G2r; data dependencies are respected; in the software-pipelined
+    order the next group's G1a sits between G1b(i) and G2r(i), and jobs alternating between two accumulators never reuse one
+    that its epilogue cannot have drained."""
+    import ctypes
+    from audiodiffuser_b200 import _native as N
+    lib = N.lib()
+    for n in (1, 2, 3, 7, 216):
+        for write_h in (0, 1):
+            for pipe in (0, 1):
+                cap = 3 * n + 2
+                types, groups = (ctypes.c_int * cap)(), (ctypes.c_int * cap)()
+                cnt = lib.adb_debug_zs_job_order(n, write_h, pipe, types, groups, cap)
+                seq = [(types[k], groups[k]) for k in range(cnt)]
+                assert cnt == (3 if write_h else 2) * n
+                pos = {job: k for k, job in enumerate(seq)}
+                assert len(pos) == cnt                                        # no job twice
+                for i in range(n):
+                    assert pos[(0, i)] < pos[(1, i)]                          # G1a before G1b
+                    if write_h:
+                        assert pos[(1, i)] < pos[(2, i)]                      # G2r needs both halves of z
+                        if i + 1 < n:
+                            assert pos[(2, i)] < pos[(1, i + 1)]              # G1b(i+1)'s epilogue overwrites z K-blocks 2, 3
+                            if pipe:
+                                assert pos[(1, i)] < pos[(0, i + 1)] < pos[(2, i)]     # independent work covers epilogue 1b
+                            else:
+                                assert pos[(2, i)] < pos[(0, i + 1)]
+                    elif i + 1 < n:
+                        assert pos[(1, i)] < pos[(0, i + 1)]
+                # accumulator k & 1: the job two positions earlier used the same one; its epilogue needs that job complete,
+                # which the in-order tensor pipe guarantees — here just check the alternation covers every job once
+                assert sorted(seq) == sorted((t, i) for i in range(n) for t in range(3 if write_h else 2))
