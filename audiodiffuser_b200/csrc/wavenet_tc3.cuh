@@ -422,12 +422,17 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                     tmem_ld_32x32(t_lane + buf * 256 + col, r);
                     tmem_ld_wait();
                     uint32_t pk[16];
+                    const float4* b4 = reinterpret_cast<const float4*>(b2g + cc * 32);      // 128-byte aligned: 8 vector loads per chunk
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const uint32_t hv = hres[cc][i >> 1];
-                        const float v0 = (__uint_as_float(r[i]) + bf16_lo(hv) + __ldg(b2g + cc * 32 + i)) * 0.70710678118654752f;
-                        const float v1 = (__uint_as_float(r[i + 1]) + bf16_hi(hv) + __ldg(b2g + cc * 32 + i + 1)) * 0.70710678118654752f;
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bb = __ldg(b4 + (i >> 2));
+                        const uint32_t h0 = hres[cc][i >> 1], h1 = hres[cc][(i >> 1) + 1];
+                        const float v0 = (__uint_as_float(r[i]) + bf16_lo(h0) + bb.x) * 0.70710678118654752f;
+                        const float v1 = (__uint_as_float(r[i + 1]) + bf16_hi(h0) + bb.y) * 0.70710678118654752f;
+                        const float v2 = (__uint_as_float(r[i + 2]) + bf16_lo(h1) + bb.z) * 0.70710678118654752f;
+                        const float v3 = (__uint_as_float(r[i + 3]) + bf16_hi(h1) + bb.w) * 0.70710678118654752f;
                         pk[i >> 1] = pack_bf16x2(v0, v1);
+                        pk[(i >> 1) + 1] = pack_bf16x2(v2, v3);
                     }
                     uint8_t* box = tbuf + (cc & 1) * 2048;
                     if (lane == 0) tma_store_wait_read<1>();       // the store that last used this box (two commits ago) has read it
