@@ -80,6 +80,13 @@ _SIGS = {
     "adb_cl_time_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "adb_cl_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_float, c_int, c_int, c_void_p]),
+    "adb_cl_gn_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_gn_coef": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                               c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
+    "adb_cl_gn_conv3": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_void_p]),
+    "adb_cl_conv_cat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_void_p]),
     "adb_cl_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
     "adb_cl_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_cl_concat": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),

@@ -179,6 +179,7 @@ class UNet1dBase(nn.Module):
         self._packed_key = None
         self._graphs = {}
         self.use_cuda_graph = True
+        self.fuse_groupnorm = True      # bf16: GroupNorm apply inside the consumer convolution (adb_cl_gn_conv3); False = separate passes
         self.graph_launches = 0          # kernel launches replayed through CUDA graphs (invisible to adb_launch_count)
 
     # ---- weight re-layout (once per parameter version) ----------------------------------------------
@@ -252,7 +253,7 @@ class UNet1dBase(nn.Module):
 
         cond_w, cond_b, cond_off = [], [], {}
 
-        def resnet(p):
+        def resnet(p, cat=False):
             co = sd[p + ".block1.project.weight"].shape[0]
             cond_off[p] = sum(t.shape[0] for t in cond_w)
             cond_w.append(sd[p + ".to_cond_embedding.1.weight"])
@@ -263,6 +264,12 @@ class UNet1dBase(nn.Module):
                 P[f"{p}.{blk}.gn"] = (sd[f"{p}.{blk}.groupnorm.weight"].contiguous(), sd[f"{p}.{blk}.groupnorm.bias"].contiguous())
             if p + ".to_out.weight" in sd:
                 P[p + ".to_out"] = conv_k(p + ".to_out.weight", p + ".to_out.bias")
+                if cat and bf16:
+                    # the block reads cat(x, skip * skip_scale) (unet1d.py:552-556) as TWO inputs: the constant goes into the
+                    # weight rows of the skip channels (the first `co` input channels are x, UpsampleBlock1d :507-509)
+                    w = sd[p + ".to_out.weight"].permute(2, 1, 0).clone()
+                    w[:, co:, :] *= 2 ** -0.5 if cfg["use_skip_scale"] else 1.0
+                    P[p + ".to_out_cat"] = gemm_weight(w, sd[p + ".to_out.bias"], dict(off0=0, dil=1, ups=0))
             P[p + ".co"] = co
 
         def transformer(p):
@@ -292,7 +299,7 @@ class UNet1dBase(nn.Module):
         for u, i in enumerate(reversed(range(n))):
             p, f = f"upsamples.{u}", cfg["factors"][i]
             for j in range(cfg["num_blocks"][i] + (1 if cfg["attentions"][i] else 0)):
-                resnet(f"{p}.blocks.{j}")
+                resnet(f"{p}.blocks.{j}", cat=True)
             if cfg["attentions"][i]:
                 transformer(p + ".transformer")
             P[p + ".upsample"] = conv_k(p + ".upsample.weight", p + ".upsample.bias") if f == 1 else \
@@ -333,7 +340,8 @@ class UNet1dBase(nn.Module):
         B, cin, L = x.shape
         groups, heads = cfg["resnet_groups"], cfg["attention_heads"]
         W, S = cfg["window_length"], cfg["stride"]
-        sums = torch.empty(B * groups * 2, dtype=torch.float64, device=dev)
+        sums = torch.zeros(B * groups * 2, dtype=torch.float64, device=dev)     # adb_cl_groupnorm clears it itself; adb_cl_gn_coef leaves it zero
+        tickets = torch.zeros(B, dtype=torch.int32, device=dev)
 
         def conv(h, ent, act=ACT_NONE, res=None):
             Bh, Lh, Ch = h.shape
@@ -367,9 +375,57 @@ class UNet1dBase(nn.Module):
             N.check(lib.adb_cl_layernorm(N.ptr(h), N.ptr(g), N.ptr(b), N.ptr(o), h.shape[0] * h.shape[1], h.shape[2], 1e-5, dt, st))
             return o
 
-        def resnet(p, h):                                        # ResnetBlock1d.forward, unet1d.py:297-316
+        def stats_ok(c, g):
+            # shapes the vectorised statistics kernel takes (adb_cl_gn_coef): 16-byte vectors inside a group, 256 threads = whole rows
+            return g >= 1 and c % g == 0 and (c // g) % 8 == 0 and g <= 64 and 256 % g == 0 and c <= 2048 and 256 % (c // 8) == 0
+
+        def fusable(c1, c2, ent1, ent2):
+            # adb_cl_gn_conv3: bf16, k = 3 "same" convolutions, 64-channel K-blocks, groups that do not straddle the two inputs
+            cin, co = c1 + c2, ent1["n"]
+            if not (bf16 and self.fuse_groupnorm and c1 % 64 == 0 and c2 % 64 == 0 and co % 64 == 0 and cin % groups == 0
+                    and c1 % (cin // groups) == 0):
+                return False
+            g1 = c1 // (cin // groups)
+            return (stats_ok(c1, g1) and (c2 == 0 or stats_ok(c2, groups - g1)) and stats_ok(co, groups)
+                    and all(e["taps"] == 3 and e["off0"] == -1 and e["dil"] == 1 and not e["ups"] and "f" not in e for e in (ent1, ent2)))
+
+        def gn_conv(h, sk, gb, ss_ptr, ss_ld, ent, res):
+            # statistics + per-channel coefficients of the raw input(s), then GroupNorm apply + SiLU inside the convolution's operand path
+            Bh, Lh, c1 = h.shape
+            c2 = sk.shape[2] if sk is not None else 0
+            cin = c1 + c2
+            g1 = c1 // (cin // groups)
+            coef = torch.empty(2, Bh, cin, dtype=torch.float32, device=dev)
+            ssp = ss_ptr if ss_ptr is not None else c_void_p(0)
+            N.check(lib.adb_cl_gn_coef(N.ptr(h), N.ptr(sums), N.ptr(tickets), N.ptr(coef), Bh, Lh, c1, g1, groups, 0, 0, cin, N.ptr(gb[0]),
+                                       N.ptr(gb[1]), ssp, ss_ld, 1e-5, 1.0, st))
+            if sk is not None:
+                N.check(lib.adb_cl_gn_coef(N.ptr(sk), N.ptr(sums), N.ptr(tickets), N.ptr(coef), Bh, Lh, c2, groups - g1, groups, g1, c1, cin,
+                                           N.ptr(gb[0]), N.ptr(gb[1]), ssp, ss_ld, 1e-5, skip_scale, st))
+            o = torch.empty(Bh, Lh, ent["n"], dtype=adt, device=dev)
+            N.check(lib.adb_cl_gn_conv3(N.ptr(h), c1, N.ptr(sk), c2, N.ptr(coef), N.ptr(ent["w"]), N.ptr(ent["bias"]), N.ptr(res), N.ptr(o),
+                                        Bh, Lh, ent["n"], st))
+            return o
+
+        def resnet(p, h, sk=None):                               # ResnetBlock1d.forward, unet1d.py:297-316
             co = P[p + ".co"]
             ss_ptr = c_void_p(ss_all.data_ptr() + 4 * P["cond_off"][p])
+            if fusable(h.shape[2], sk.shape[2] if sk is not None else 0, P[p + ".block1"], P[p + ".block2"]) and \
+                    (sk is None or (p + ".to_out_cat") in P):
+                if sk is not None:                               # residual branch on the never-materialised concatenation
+                    ent = P[p + ".to_out_cat"]
+                    r = torch.empty(h.shape[0], h.shape[1], ent["n"], dtype=adt, device=dev)
+                    N.check(lib.adb_cl_conv_cat(N.ptr(h), h.shape[2], N.ptr(sk), sk.shape[2], N.ptr(ent["w"]), N.ptr(ent["bias"]),
+                                                N.ptr(None), N.ptr(r), h.shape[0], h.shape[1], ent["n"], 1, 0, 1, ACT_NONE, st))
+                else:
+                    r = conv(h, P[p + ".to_out"]) if (p + ".to_out") in P else h
+                a = gn_conv(h, sk, P[p + ".block1.gn"], None, 0, P[p + ".block1"], None)
+                return gn_conv(a, None, P[p + ".block2.gn"], ss_ptr, ss_all.shape[1], P[p + ".block2"], r)
+            if sk is not None:
+                cat = torch.empty(h.shape[0], h.shape[1], h.shape[2] + sk.shape[2], dtype=adt, device=dev)
+                N.check(lib.adb_cl_concat(N.ptr(h), N.ptr(sk), skip_scale, N.ptr(cat), h.shape[0] * h.shape[1], h.shape[2],
+                                          sk.shape[2], dt, st))
+                h = cat
             r = conv(h, P[p + ".to_out"]) if (p + ".to_out") in P else h
             a = conv(gn(h, P[p + ".block1.gn"]), P[p + ".block1"])
             assert a.shape[2] == co
@@ -465,11 +521,7 @@ class UNet1dBase(nn.Module):
             p = f"upsamples.{u}"
             skips = skips_list.pop()
             for j in range(cfg["num_blocks"][i] + (1 if cfg["attentions"][i] else 0)):
-                sk = skips.pop()
-                cat = torch.empty(h.shape[0], h.shape[1], h.shape[2] + sk.shape[2], dtype=adt, device=dev)
-                N.check(lib.adb_cl_concat(N.ptr(h), N.ptr(sk), skip_scale, N.ptr(cat), h.shape[0] * h.shape[1], h.shape[2],
-                                          sk.shape[2], dt, st))
-                h = resnet(f"{p}.blocks.{j}", cat)
+                h = resnet(f"{p}.blocks.{j}", h, skips.pop())     # cat(h, skip * skip_scale), unet1d.py:552-556
             if cfg["attentions"][i]:
                 h = transformer(p + ".transformer", h)
             h = conv(h, P[p + ".upsample"])

@@ -22,6 +22,7 @@
 #include "wavenet_tc3.cuh"
 #include "cl_ops.cuh"
 #include "cl_conv_tc.cuh"
+#include "cl_conv_gn_tc.cuh"
 #include "train_kernels.cuh"
 #include "train_tc.cuh"
 

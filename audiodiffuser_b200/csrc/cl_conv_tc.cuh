@@ -47,6 +47,8 @@ struct ClConvTcParams {
     int tiles_n;            // N / NT
     int kb_per_tap;         // Cin / 64
     int epi_warps;          // 4 (block of 192 threads) or 8 (block of 320): the fused gate epilogues need the second set
+    int kb1;                // K-blocks per tap that come from the first input; the rest from the second (channel concatenation
+                            // of two tensors, unet1d.py:552-556); = kb_per_tap for a single input
 };
 
 // EPI_WARPS = 4 (192 threads) for the plain / transposed / WAVdec stores; EPI_WARPS = 8 (320 threads) with FUSED = true adds
@@ -68,7 +70,8 @@ __device__ __forceinline__ void ct_load64(const __nv_bfloat16* src, uint32_t (&v
 
 template <int EPI_WARPS, bool FUSED>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
-cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const ClConvTcParams p) {
+cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_in2,
+                  const __grid_constant__ CUtensorMap tm_w, const ClConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_bias = reinterpret_cast<float*>(smem + CT_STAGES * CT_STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CT_STAGES * CT_STAGE_BYTES + 1024);
@@ -80,7 +83,7 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ClConvArgs& a = p.a;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_in); tma_prefetch_desc(&tm_w); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_in); tma_prefetch_desc(&tm_in2); tma_prefetch_desc(&tm_w); }
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
@@ -110,7 +113,8 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                     uint8_t* sa = smem + stage * CT_STAGE_BYTES;
                     const int tap = kb / p.kb_per_tap, cib = kb % p.kb_per_tap;
                     mbar_arrive_expect_tx(&bar_full[stage], stage_tx);
-                    tma_load_3d(sa, &tm_in, &bar_full[stage], cib * 64, t0 + a.off0 + tap * a.dil, b);
+                    if (cib < p.kb1) tma_load_3d(sa, &tm_in, &bar_full[stage], cib * 64, t0 + a.off0 + tap * a.dil, b);
+                    else             tma_load_3d(sa, &tm_in2, &bar_full[stage], (cib - p.kb1) * 64, t0 + a.off0 + tap * a.dil, b);
                     tma_load_2d(sa + CT_A_BYTES, &tm_w, &bar_full[stage], 0, kb * a.N + n0);
                 }
                 __syncwarp();

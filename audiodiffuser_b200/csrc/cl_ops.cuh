@@ -213,12 +213,13 @@ __global__ void cl_cast_to_f32_kernel(const __nv_bfloat16* __restrict__ in, floa
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm (nn.GroupNorm(num_groups, C), unet1d.py:179) over (C/G channels x L) per sample.
-//   pass 1: fp64 sum / sum of squares per (b, g) -> sums[b][g][2] (zeroed by the caller)
+//   pass 1: fp64 sum / sum of squares per (b, g) -> sums[b][g_off + g][2] of a [B][g_total][2] array (zeroed by the caller;
+//           g_off / g_total place the groups of one half of a channel concatenation next to the other half's)
 //   pass 2: y = (x - mean) * rstd * gamma + beta ; optional y = y * (scale + 1) + shift (unet1d.py:160-161) ; act
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) cl_gn_stats_kernel(const T* __restrict__ in, double* __restrict__ sums, int L, int C,
-                                                          int G, int chunks) {
+                                                          int G, int chunks, int g_total, int g_off) {
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cpg = C / G;
     const int rows_per = (L + chunks - 1) / chunks;
@@ -246,8 +247,8 @@ __global__ void __launch_bounds__(256) cl_gn_stats_kernel(const T* __restrict__ 
         if (threadIdx.x == 0) {
             double a = 0.0, c = 0.0;
             for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += red[0][w]; c += red[1][w]; }
-            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2], a);
-            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2 + 1], c);
+            atomicAdd(&sums[(static_cast<long long>(b) * g_total + g_off + g) * 2], a);
+            atomicAdd(&sums[(static_cast<long long>(b) * g_total + g_off + g) * 2 + 1], c);
         }
         __syncthreads();
     }
@@ -608,9 +609,25 @@ template <> struct ClVec<__nv_bfloat16> {
 // its chunk (4 independent loads in flight); fp32 partial sums over <= 16 rows are promoted to fp64; the block
 // combines per group with warp shuffles (fp64) and issues 2 global atomics per group.
 // Needs (C / G) % VEC == 0, 256 % (C / VEC) == 0, (256 / G) threads per group. grid (chunks, B).
+// Optional last stage of cl_gn_stats_vec_kernel (the fused GroupNorm-apply convolution, cl_conv_gn_tc.cuh): the block that
+// finishes a sample LAST turns the group sums into the per-channel affine coefficients the convolution's transform warps
+// apply (the arithmetic of cl_gn_apply_vec_kernel; `scale` = a constant factor on this input, folded into statistics and
+// slope), stored HALVED because the consumer evaluates SiLU(y) = h tanh(h) + h with h = y / 2. It then re-zeroes its sums and
+// its ticket, so neither needs a memset between uses.
+struct GnCoefArgs {
+    float* coef;            // [2][B][Cin_total]: slopes, then offsets; nullptr = statistics only
+    int* tickets;           // [B], zero before the first use
+    const float* gamma;     // [Cin_total]
+    const float* beta;      // [Cin_total]
+    const float* ss;        // [B][ss_ld]: scale at [c], shift at [Cin_total + c] (c over the concatenated channels), or nullptr
+    long long ss_ld;
+    float eps, scale;
+    int c_off, Cin_total, B;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) cl_gn_stats_vec_kernel(const T* __restrict__ in, double* __restrict__ sums, int L, int C,
-                                                              int G, int chunks) {
+                                                              int G, int chunks, int g_total, int g_off, GnCoefArgs fin) {
     constexpr int VE = ClVec<T>::N;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cpg = C / G, vpr = C / VE;
@@ -667,10 +684,44 @@ __global__ void __launch_bounds__(256) cl_gn_stats_vec_kernel(const T* __restric
             c += __shfl_xor_sync(0xffffffffu, c, o);
         }
         if (lane == 0) {
-            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2], a);
-            atomicAdd(&sums[(static_cast<long long>(b) * G + g) * 2 + 1], c);
+            atomicAdd(&sums[(static_cast<long long>(b) * g_total + g_off + g) * 2], a);
+            atomicAdd(&sums[(static_cast<long long>(b) * g_total + g_off + g) * 2 + 1], c);
         }
     }
+    if (fin.coef == nullptr) return;
+    __shared__ int s_last;
+    __shared__ float s_mean[64], s_rstd[64];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&fin.tickets[b], 1) == static_cast<int>(gridDim.x) - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < G) {
+        double* sp = sums + (static_cast<long long>(b) * g_total + g_off + threadIdx.x) * 2;
+        const double cnt = static_cast<double>(cpg) * L, sc = static_cast<double>(fin.scale);
+        const double mean = sc * (__ldcg(sp) / cnt);
+        const double var = fmax(sc * sc * (__ldcg(sp + 1) / cnt) - mean * mean, 0.0);
+        s_mean[threadIdx.x] = static_cast<float>(mean);
+        s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(fin.eps)));
+        sp[0] = 0.0; sp[1] = 0.0;
+    }
+    __syncthreads();
+    float* ca = fin.coef + static_cast<long long>(b) * fin.Cin_total + fin.c_off;
+    float* cb = ca + static_cast<long long>(fin.B) * fin.Cin_total;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int cg = fin.c_off + c;
+        float a = s_rstd[c / cpg] * fin.gamma[cg];
+        float bb = fin.beta[cg] - s_mean[c / cpg] * a;
+        if (fin.ss) {
+            const float sc = fin.ss[static_cast<long long>(b) * fin.ss_ld + cg] + 1.0f, sh = fin.ss[static_cast<long long>(b) * fin.ss_ld + fin.Cin_total + cg];
+            a *= sc;
+            bb = fmaf(bb, sc, sh);
+        }
+        ca[c] = 0.5f * a * fin.scale;          // the slope acts on the raw (unscaled) input
+        cb[c] = 0.5f * bb;
+    }
+    if (threadIdx.x == 0) fin.tickets[b] = 0;
 }
 
 // GroupNorm apply: per-group mean / rstd are finished in fp64 by G threads, per-channel affine coefficients

@@ -130,7 +130,9 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
         TC_DBG_T0(tp_all);
         for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
             const int tile = grp * 2 + rank;
-            const int b = tile / p.tiles_per_b;           // >= B for a padding tile: TMA zero-fills
+            const int b_real = tile / p.tiles_per_b;      // >= B for a padding tile: TMA zero-fills
+            // 2048 (timing experiment): every activation / skip access confined to a window of (dbg >> 16) samples (L2-resident)
+            const int b = ((kdbg & 2048) && b_real < p.B) ? b_real % (kdbg >> 16) : b_real;
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
             if ((kdbg & 4) && lane < 4 && grp + num_pairs < num_groups) {
                 // warm L2 with the centre-tap rows of this CTA's NEXT tile (first touch of those rows: the dilated
@@ -262,7 +264,7 @@ wavenet_block_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid
         for (int grp = pair_id; grp < num_groups; grp += num_pairs) {
             const int tile = grp * 2 + rank;
             const bool tile_valid = tile < p.num_tiles;
-            const int b = tile / p.tiles_per_b;
+            const int b = (kdbg & 2048) ? (tile / p.tiles_per_b) % (kdbg >> 16) : tile / p.tiles_per_b;
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
             const int t = t0 + row;
             named_bar_sync(1, TC_EPI_THREADS);

@@ -258,6 +258,31 @@ int adb_cl_time_features(const float* t_dev, const float* w_dev, float* out_dev,
 int adb_cl_groupnorm(const void* in_dev, const float* gamma_dev, const float* beta_dev, const float* scale_shift_dev,
                      int64_t ss_ld, void* out_dev, double* sums_ws_dev, int B, int L, int C, int G, float eps, int act,
                      int dtype, void* stream);
+/* GroupNorm statistics only: fp64 (sum, sum of squares) of the G groups of in_dev [B][L][C] into
+ * sums_dev[b][g_off + g][2] of a [B][g_total][2] array (g_off / g_total place the groups of one half of a channel concatenation
+ * next to the other half's, unet1d.py:552-556). zero_first != 0 clears the whole array first. */
+int adb_cl_gn_stats(const void* in_dev, double* sums_dev, int B, int L, int C, int G, int g_total, int g_off, int zero_first,
+                    int dtype, void* stream);
+/* First half of the fused ConvBlock1d (bf16 only): GroupNorm statistics of in_dev [B][L][C] (G groups -> sums_dev[b][g_off + g] of a
+ * [B][g_total][2] fp64 array) and, by the block that finishes a sample last, the per-(sample, channel) affine coefficients of
+ * GroupNorm * gamma + beta followed by x * (scale + 1) + shift (unet1d.py:160-161, :195-207) into coef_dev [2][B][Cin_total]
+ * (slopes, then offsets; channel c of this input is channel c_off + c of the possibly concatenated tensor, unet1d.py:552-556;
+ * `scale` = a constant factor on this input, e.g. the skip scale 2^-1/2). sums_dev and tickets_dev ([B] int32) must be zero
+ * before the first call and are left zero. scale_shift_dev as in adb_cl_groupnorm (indexed over the concatenated channels). */
+int adb_cl_gn_coef(const void* in_dev, double* sums_dev, int* tickets_dev, float* coef_dev, int B, int L, int C, int G, int g_total,
+                   int g_off, int c_off, int Cin_total, const float* gamma_dev, const float* beta_dev, const float* scale_shift_dev,
+                   int64_t ss_ld, float eps, float scale, void* stream);
+/* Second half: out = bias + res + Conv1d_k3_same(SiLU(slope * x + offset)) with the activation applied inside the convolution's
+ * operand path, so the normalised tensor (and the concatenation) never exists in HBM (unet1d.py:186-193, the residual add of
+ * ResnetBlock1d :315). x = in1_dev [B][L][C1], or the channel concatenation [in1 | in2] (in2_dev [B][L][C2], NULL / 0 for one
+ * input); coef_dev from adb_cl_gn_coef over C1 + C2 channels; w_packed_dev from adb_cl_pack_conv_weights(C1 + C2, N, 3). */
+int adb_cl_gn_conv3(const void* in1_dev, int C1, const void* in2_dev, int C2, const float* coef_dev, const void* w_packed_dev,
+                    const float* bias_dev, const void* res_dev, void* out_dev, int B, int L, int N, void* stream);
+/* adb_cl_conv (bf16, plain store) over the channel concatenation of two inputs that is never materialised: K-blocks of the first
+ * C1 channels come from in1_dev [B][L][C1], the rest from in2_dev [B][L][C2]; a constant factor on the second input is folded
+ * into the packed weights by the caller (ResnetBlock1d.to_out on cat(x, skip * 2^-1/2), unet1d.py:291-295, :552-556). */
+int adb_cl_conv_cat(const void* in1_dev, int C1, const void* in2_dev, int C2, const void* w_packed_dev, const float* bias_dev,
+                    const void* res_dev, void* out_dev, int B, int L, int N, int taps, int off0, int dil, int act, void* stream);
 /* row-wise LayerNorm over C (nn.LayerNorm unet1d.py:79 with b_dev; LayerNorm1d unet1d.py:32-45 with b_dev = NULL) */
 int adb_cl_layernorm(const void* in_dev, const float* g_dev, const float* b_dev, void* out_dev, int64_t rows, int C, float eps,
                      int dtype, void* stream);

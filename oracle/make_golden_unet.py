@@ -1,7 +1,7 @@
 """Generate tests/golden/unet1d_*.npz by running the REFERENCE's own UNet1dBase / EluDiffusion / EDMSampler
 (build container only; see oracle/make_golden.py for the conventions).
 
-    python -m oracle.make_golden_unet
+    python -m oracle.make_golden_unet [case ...]
 """
 import importlib
 import os
@@ -32,7 +32,10 @@ def main():
     torch.set_num_threads(os.cpu_count())
     ref = import_reference()
     R = importlib.import_module("src.models.backbones.unet1d")
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]           # optional: regenerate just the named cases
     for name, (cfg, B, L, seed) in CASES.items():
+        if only and name not in only:
+            continue
         net, sd = build_ref(R, cfg, seed)
         x = seeded((B, cfg["in_channels"], L), seed + 1000)
         t = seeded((B,), seed + 2000, 1.5)
@@ -40,6 +43,8 @@ def main():
         assert torch.equal(ounet.unet1d_forward(sd, cfg, x, t), out), "oracle no longer bit-identical to the reference"
         save(name, x=x, t=t, out=out, cfg=np.array([B, L, seed], dtype=np.int64))
 
+    if only:
+        return
     # denoiser + sampler through the reference's own EluDiffusion / EDMSampler (no adapter needed)
     cfg, B, L, seed, steps = UNET_MID, 2, 4096, 105, 5
     net, sd = build_ref(R, cfg, seed)

@@ -106,6 +106,7 @@ UNET_CASES = {   # name: (cfg, B, L, seed)
     "unet1d_small_ragged": (UNET_SMALL, 3, 96, 102),         # L/stride/f0/f1 = 3 rows at the bottom: tiles far from full
     "unet1d_mid": (UNET_MID, 2, 16384, 103),
     "unet1d_cfg4_l65536": (UNET1D_CONFIG4, 1, 65536, 104),   # SURVEY §8(d) config 4 architecture at a quarter of the length
+    "unet1d_cfg4_l262144": (UNET1D_CONFIG4, 1, 262144, 107),  # BASELINE.json configs[3] at its real length: 2 x 262144, B = 1
 }
 
 

@@ -29,6 +29,7 @@ def make_unet(cfg, seed, precision, dev):
     ("unet1d_small_ragged", ["fp32"]),
     ("unet1d_mid", ["fp32", "bf16"]),
     ("unet1d_cfg4_l65536", ["fp32", "bf16"]),   # BASELINE config 4 architecture (102 M parameters)
+    ("unet1d_cfg4_l262144", ["fp32", "bf16"]),  # the same at the config's real length, 2 x 262144
 ])
 def test_unet_vs_reference_golden(dev, name, precisions):
     from audiodiffuser_b200 import _native as N
@@ -44,6 +45,7 @@ def test_unet_vs_reference_golden(dev, name, precisions):
         assert out.shape == (B, cfg["in_channels"], L)
         e = rel_l2(out, g["out"])
         print(f"{name} {precision}: rel-L2 {e:.3e}")
+        record_parity(f"{name}_{precision}", rel_l2_vs_reference=e)
         assert e < TOL[precision], (precision, e)
         net.use_cuda_graph = True               # the captured graph must reproduce the eager launch sequence exactly
         out_g = net(x, t)

@@ -14,6 +14,7 @@ net = UNet1dBase(precision=prec, **UNET1D_CONFIG4)
 net.load_state_dict(make_unet1d_state_dict(UNET1D_CONFIG4, 0), strict=True)
 net = net.to(dev)
 net.use_cuda_graph = os.environ.get("ADB_NO_GRAPH") is None
+net.fuse_groupnorm = os.environ.get("ADB_UNET_NOFUSE") is None      # tools only: time the separate GroupNorm passes
 x = torch.randn(B, 2, L, device=dev); t = torch.zeros(B, device=dev)
 for _ in range(2): y = net(x, t)
 _native.check_async()
@@ -23,4 +24,4 @@ for _ in range(reps): net(x, t)
 e1.record(); torch.cuda.synchronize(); wall = (time.perf_counter() - t0) / reps
 ms = e0.elapsed_time(e1) / reps
 fl = 61.69e9 * B * L / 262144
-print(f"unet1d cfg4 B={B} L={L} {prec} graph={net.use_cuda_graph}: {ms:.3f} ms/eval device, {wall*1e3:.3f} ms wall -> {fl/ms/1e9:.1f} TFLOP/s")
+print(f"unet1d cfg4 B={B} L={L} {prec} graph={net.use_cuda_graph} fuse_gn={net.fuse_groupnorm}: {ms:.3f} ms/eval device, {wall*1e3:.3f} ms wall -> {fl/ms/1e9:.1f} TFLOP/s")
