@@ -410,6 +410,7 @@ struct adb_wavenet {
     // The training forward and the per-block debug entry point always use the pair kernel (they need every block's skip sum).
     int block_kernel = 3;
     int zs_pipe = 1;                            // z-stash kernel: software-pipelined job order (ADB_ZS_PIPE=0: plain per-group order)
+    int zs_hi_roles = 0;                        // z-stash kernel: producer / MMA issuer on the highest warp ids (ADB_ZS_HI_ROLES)
     int pair = 1;                               // derived: block_kernel != 0
     int no_stash = 0;                           // derived: block_kernel == 1
     int chunk = 256;                            // samples per pass of the bf16 stack (ADB_CHUNK): bounds the workspace
@@ -749,6 +750,8 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             n->no_stash = n->block_kernel == 1;
             const char* pe = getenv("ADB_ZS_PIPE");
             if (pe) n->zs_pipe = atoi(pe) != 0;
+            const char* he = getenv("ADB_ZS_HI_ROLES");
+            if (he) n->zs_hi_roles = atoi(he) != 0;
             const char* fe = getenv("ADB_FUSE_TAIL");
             if (fe) n->fuse_tail = atoi(fe) != 0;
             const char* ce = getenv("ADB_CHUNK");
@@ -994,6 +997,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
                 bp.write_h = (l + 1 < layers) ? 1 : 0;
                 bp.zrow0 = slot * bc;
+                bp.hi_roles = n->zs_hi_roles;
                 bp.dbg = n->dbg;
                 lc.dynamicSmemBytes = TC3_SMEM_BYTES;
                 if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true>, m_h, n->tm_w2, m_hout, m_zst, bp));

@@ -56,6 +56,7 @@ struct BlockZsParams {
     int tiles_per_b, num_tiles;
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
     int zrow0;                      // first "batch" coordinate of this layer's slot in the stash map (slot * B)
+    int hi_roles;                   // 1: producer / MMA issuer on warps 8 / 9 (highest scheduler priority), epilogue on 0..7
     int dbg;                        // ADB_DEBUG builds only: 2 = in-kernel cycle accounting; timing experiments (results wrong):
                                     // 4 no A re-load for G1b, 8 no stash stores, 16 no h' stores, 32 no gate math, 64 no residual read,
                                     // 1024 all stores to a fixed L2-resident tile per CTA
@@ -104,14 +105,17 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     const int lane = threadIdx.x & 31;
     const int rank = static_cast<int>(cluster_ctarank());
     const bool leader = rank == 0;
+    // warp roles: the scheduler arbitrates highest-warp-id-first, so with hi_roles the two single-thread roles (TMA producer, MMA
+    // issuer) take warps 8 / 9 and never wait behind the eight epilogue warps (0..7); otherwise warps 0 / 1 and epilogue 2..9
+    const int w_prod = p.hi_roles ? 8 : 0, w_mma = p.hi_roles ? 9 : 1, ew0 = p.hi_roles ? 0 : 2;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == w_prod && lane == 0) {
         tma_prefetch_desc(&tm_h);
         tma_prefetch_desc(&tm_w);
         tma_prefetch_desc(&tm_hout);
         tma_prefetch_desc(&tm_zst);
     }
-    if (warp == 1) {
+    if (warp == w_mma) {
         if (lane == 0) {
             for (int s = 0; s < T3_STAGES; ++s) { mbar_init(&bar_full[s], 2); mbar_init(&bar_empty[s], 1); }
             for (int i = 0; i < 2; ++i) {
@@ -139,7 +143,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     const int n_mine = (num_groups - pair_id + num_pairs - 1) / num_pairs;     // tile groups of this CTA pair (>= 1)
     const int n_slots = zs_num_slots<PIPE>(n_mine, p.write_h);
 
-    if (warp == 0) {
+    if (warp == w_prod) {
         // ===================== TMA producer (both CTAs) =====================
         uint32_t stage = 0, phase = 0;
         long long dbg_acc[12] = {};
@@ -177,7 +181,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         }
         TC_DBG_ACC(6, tp_all);
         if ((kdbg & 2) && lane == 0 && leader) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
-    } else if (warp == 1) {
+    } else if (warp == w_mma) {
         if (leader) {
             // ===================== MMA issuer (rank 0 only) =====================
             uint32_t stage = 0, phase = 0;
@@ -235,7 +239,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         }
     } else {
         // ===================== epilogue warps (both CTAs) =====================
-        const int ew = warp - 2;
+        const int ew = warp - ew0;
         const int q = warp & 3;               // TMEM lane quarter this warp may access
         const int half = ew >> 2;             // which half of the columns this warp handles
         const int row = q * 32 + lane;
@@ -301,7 +305,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 if (job == 0) {
                     // interior tiles (every row sees all three taps) add ONE vector: E0 + E1 + E2, gate half pre-scaled by 1/2
                     named_bar_sync(1, TC_EPI_THREADS);            // everyone is done with the previous group's vector
-                    for (int i = threadIdx.x - 64; i < 512; i += TC_EPI_THREADS)
+                    for (int i = threadIdx.x - 32 * ew0; i < 512; i += TC_EPI_THREADS)
                         s_esum[i] = (Eg[i] + Eg[512 + i] + Eg[1024 + i]) * (i < 256 ? 0.5f : 1.0f);
                     named_bar_sync(1, TC_EPI_THREADS);
                 }
@@ -459,7 +463,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             }
         }
         TC_DBG_ACC(11, te_all);
-        if ((kdbg & 2) && warp == 2 && lane == 0 && leader)
+        if ((kdbg & 2) && ew == 0 && lane == 0 && leader)
             for (int i = 7; i < 12; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores fully performed before exit
     }
@@ -467,7 +471,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) {
+    if (warp == w_mma) {
         tc_fence_after_sync();
         tmem_dealloc_pair(tmem_base, 512);
     }
