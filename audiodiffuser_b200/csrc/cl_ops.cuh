@@ -694,14 +694,26 @@ __global__ void __launch_bounds__(256) cl_gn_stats_vec_kernel(const T* __restric
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&fin.tickets[b], 1) == static_cast<int>(gridDim.x) - 1;
+    // the affine parameters of this thread's first two channels do not depend on the sums: request them before the ticket
+    // result is known (the tail of the last block is latency, one L2 round trip shorter this way)
+    float pg[2], pb[2], psc[2], psh[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int c = threadIdx.x + 256 * k, cg = fin.c_off + c;
+        const bool ok = c < C;
+        pg[k] = ok ? fin.gamma[cg] : 0.f;
+        pb[k] = ok ? fin.beta[cg] : 0.f;
+        psc[k] = (ok && fin.ss) ? fin.ss[static_cast<long long>(b) * fin.ss_ld + cg] + 1.0f : 1.0f;
+        psh[k] = (ok && fin.ss) ? fin.ss[static_cast<long long>(b) * fin.ss_ld + fin.Cin_total + cg] : 0.f;
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x < G) {
         double* sp = sums + (static_cast<long long>(b) * g_total + g_off + threadIdx.x) * 2;
-        const double cnt = static_cast<double>(cpg) * L, sc = static_cast<double>(fin.scale);
-        const double mean = sc * (__ldcg(sp) / cnt);
-        const double var = fmax(sc * sc * (__ldcg(sp + 1) / cnt) - mean * mean, 0.0);
+        const double inv = 1.0 / (static_cast<double>(cpg) * L), sc = static_cast<double>(fin.scale);
+        const double mean = sc * (__ldcg(sp) * inv);
+        const double var = fmax(sc * sc * (__ldcg(sp + 1) * inv) - mean * mean, 0.0);
         s_mean[threadIdx.x] = static_cast<float>(mean);
         s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(fin.eps)));
         sp[0] = 0.0; sp[1] = 0.0;
@@ -709,15 +721,17 @@ __global__ void __launch_bounds__(256) cl_gn_stats_vec_kernel(const T* __restric
     __syncthreads();
     float* ca = fin.coef + static_cast<long long>(b) * fin.Cin_total + fin.c_off;
     float* cb = ca + static_cast<long long>(fin.B) * fin.Cin_total;
-    for (int c = threadIdx.x; c < C; c += 256) {
+    for (int c = threadIdx.x, k = 0; c < C; c += 256, ++k) {
         const int cg = fin.c_off + c;
-        float a = s_rstd[c / cpg] * fin.gamma[cg];
-        float bb = fin.beta[cg] - s_mean[c / cpg] * a;
-        if (fin.ss) {
-            const float sc = fin.ss[static_cast<long long>(b) * fin.ss_ld + cg] + 1.0f, sh = fin.ss[static_cast<long long>(b) * fin.ss_ld + fin.Cin_total + cg];
-            a *= sc;
-            bb = fmaf(bb, sc, sh);
+        float g_, b_, sc = 1.0f, sh = 0.f;
+        if (k < 2) { g_ = pg[k & 1]; b_ = pb[k & 1]; sc = psc[k & 1]; sh = psh[k & 1]; }
+        else {
+            g_ = fin.gamma[cg]; b_ = fin.beta[cg];
+            if (fin.ss) { sc = fin.ss[static_cast<long long>(b) * fin.ss_ld + cg] + 1.0f; sh = fin.ss[static_cast<long long>(b) * fin.ss_ld + fin.Cin_total + cg]; }
         }
+        float a = s_rstd[c / cpg] * g_;
+        float bb = b_ - s_mean[c / cpg] * a;
+        if (fin.ss) { a *= sc; bb = fmaf(bb, sc, sh); }
         ca[c] = 0.5f * a * fin.scale;          // the slope acts on the raw (unscaled) input
         cb[c] = 0.5f * bb;
     }

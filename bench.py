@@ -322,7 +322,8 @@ def run_unet(args, rank, world, local_rank):
                 "ms_per_network_evaluation": ms_res / args.steps / nfe, "clocks": clk}
         peaks = load_peaks()
         per_gpu = line["effective_tflops"] / world
-        line["roofline"] = {"bound": "tensor", "kernel": "whole network evaluation (cl_conv_tc_kernel is 62 % of it at B=128, GroupNorm 24 %, profiles/r1_launches_unet1d_b128.csv)",
+        line["roofline"] = {"bound": "tensor", "kernel": "whole network evaluation (at B=128: cl_conv3_gn_tc_kernel, the convolutions with GroupNorm apply + SiLU in their operand path, 43 %; "
+                                                         "cl_conv_tc_kernel 32 %; GroupNorm statistics 12 %; profiles/r2_launches_unet1d_b128.csv)",
                             "achieved": per_gpu, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s (per GPU)",
                             "frac": per_gpu / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"]}
         if not args.no_cpu_baseline and world == 1:       # host baseline: rank 0 at N = 1 only
