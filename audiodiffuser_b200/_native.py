@@ -73,6 +73,7 @@ _SIGS = {
                             c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_cl_conv_packed_elems": (c_int64, [c_int, c_int, c_int]),
     "adb_cl_pack_conv_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_pack_conv_weights_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "adb_cl_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "adb_cl_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_cl_cast": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),

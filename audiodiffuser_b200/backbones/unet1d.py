@@ -260,6 +260,14 @@ class UNet1dBase(nn.Module):
             cond_b.append(sd[p + ".to_cond_embedding.1.bias"])
             P[p + ".block1"] = conv_k(p + ".block1.project.weight", p + ".block1.project.bias")
             P[p + ".block2"] = conv_k(p + ".block2.project.weight", p + ".block2.project.bias")
+            if bf16:
+                # fp16 copy of the packed weights for the fused GroupNorm convolution (its activation operand is produced in fp16)
+                for blk in ("block1", "block2"):
+                    ent = P[f"{p}.{blk}"]
+                    if ent["cin"] % 64 == 0 and ent["n"] % 64 == 0:
+                        w16 = torch.empty(lib.adb_cl_conv_packed_elems(ent["cin"], ent["n"], ent["taps"]), dtype=torch.float16, device=dev)
+                        N.check(lib.adb_cl_pack_conv_weights_f16(N.ptr(ent["_keep"]), N.ptr(w16), ent["cin"], ent["n"], ent["taps"], st))
+                        ent["w16"] = w16
             for blk in ("block1", "block2"):
                 P[f"{p}.{blk}.gn"] = (sd[f"{p}.{blk}.groupnorm.weight"].contiguous(), sd[f"{p}.{blk}.groupnorm.bias"].contiguous())
             if p + ".to_out.weight" in sd:
@@ -387,7 +395,8 @@ class UNet1dBase(nn.Module):
                 return False
             g1 = c1 // (cin // groups)
             return (stats_ok(c1, g1) and (c2 == 0 or stats_ok(c2, groups - g1)) and stats_ok(co, groups)
-                    and all(e["taps"] == 3 and e["off0"] == -1 and e["dil"] == 1 and not e["ups"] and "f" not in e for e in (ent1, ent2)))
+                    and all(e["taps"] == 3 and e["off0"] == -1 and e["dil"] == 1 and not e["ups"] and "f" not in e and "w16" in e
+                            for e in (ent1, ent2)))
 
         def gn_conv(h, sk, gb, ss_ptr, ss_ld, ent, res):
             # statistics + per-channel coefficients of the raw input(s), then GroupNorm apply + SiLU inside the convolution's operand path
@@ -403,7 +412,7 @@ class UNet1dBase(nn.Module):
                 N.check(lib.adb_cl_gn_coef(N.ptr(sk), N.ptr(sums), N.ptr(tickets), N.ptr(coef), Bh, Lh, c2, groups - g1, groups, g1, c1, cin,
                                            N.ptr(gb[0]), N.ptr(gb[1]), ssp, ss_ld, 1e-5, skip_scale, st))
             o = torch.empty(Bh, Lh, ent["n"], dtype=adt, device=dev)
-            N.check(lib.adb_cl_gn_conv3(N.ptr(h), c1, N.ptr(sk), c2, N.ptr(coef), N.ptr(ent["w"]), N.ptr(ent["bias"]), N.ptr(res), N.ptr(o),
+            N.check(lib.adb_cl_gn_conv3(N.ptr(h), c1, N.ptr(sk), c2, N.ptr(coef), N.ptr(ent["w16"]), N.ptr(ent["bias"]), N.ptr(res), N.ptr(o),
                                         Bh, Lh, ent["n"], st))
             return o
 

@@ -3,7 +3,8 @@
 // adds the residual). bf16 activations [B][L][C] channels-last, fp32 accumulation in TMEM.
 //
 //   Y[b][t][n] = bias[n] (+ res[b][t][n]) + sum_tap sum_ci Xn[b][t + tap - 1][ci] W[tap][ci][n]
-//   Xn[b][r][ci] = 0 <= r < L ? bf16(SiLU(ca[b][ci] X[b][r][ci] + cb[b][ci])) : 0      (zero padding AFTER the activation)
+//   Xn[b][r][ci] = 0 <= r < L ? fp16(SiLU(ca[b][ci] X[b][r][ci] + cb[b][ci])) : 0      (zero padding AFTER the activation;
+//                                fp16, not bf16: the operand never reaches HBM, so its format is free, W is packed in fp16 too)
 //
 // The normalised tensor never exists in HBM (the unfused path writes and re-reads it: 17 % of a config-4 evaluation).
 // A naive operand-path transform would run once per tap and box; here each K-block [64 ch] of a tile is staged ONCE with its
@@ -56,6 +57,7 @@ struct GcSmem {
     static constexpr int total = tmem_ptr + 16;
 };
 static_assert(GcSmem::b % 1024 == 0, "swizzle alignment");
+static_assert(GC_SA % 2 == 0 && GC_XF_WARPS == 8, "two transform groups of four warps walk the slots of one parity each");
 static_assert(GcSmem::total <= 232448, "shared memory budget");
 constexpr int GC_SMEM_BYTES = GcSmem::total;
 
@@ -94,7 +96,7 @@ cl_conv3_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_in1, const __grid_c
     if (warp == GC_WARP_PROD && lane == 0) { tma_prefetch_desc(&tm_in1); tma_prefetch_desc(&tm_in2); tma_prefetch_desc(&tm_w); }
     if (warp == GC_WARP_MMA) {
         if (lane == 0) {
-            for (int s = 0; s < GC_SA; ++s) { mbar_init(&bar_araw[s], 1); mbar_init(&bar_aready[s], 2 * GC_XF_WARPS); mbar_init(&bar_aempty[s], 1); }
+            for (int s = 0; s < GC_SA; ++s) { mbar_init(&bar_araw[s], 1); mbar_init(&bar_aready[s], GC_XF_WARPS /* 2 CTAs x the 4 warps of one transform group */); mbar_init(&bar_aempty[s], 1); }
             for (int s = 0; s < GC_SB; ++s) { mbar_init(&bar_bfull[s], 2); mbar_init(&bar_bempty[s], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 2 * GC_EPI_WARPS); }
             fence_mbar_init();
@@ -171,7 +173,7 @@ cl_conv3_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_in1, const __grid_c
         if (leader) {
             // ===================== MMA issuer (rank 0 only) =====================
             uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
-            const uint32_t idesc = umma_idesc_pair_bf16(static_cast<uint32_t>(p.NT));
+            const uint32_t idesc = umma_idesc_pair_f16(static_cast<uint32_t>(p.NT));     // fp16 x fp16 -> fp32
             long long dbg_acc[16] = {};
             TC_DBG_T0(tm_all);
             for (int gi = 0; gi < my_groups; ++gi) {
@@ -287,19 +289,24 @@ cl_conv3_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_in1, const __grid_c
     } else {
         // ===================== transform warps (both CTAs): raw box -> SiLU(ca x + cb), rows outside the sample -> 0 =====================
         const int tt = threadIdx.x - 32 * GC_EPI_WARPS;               // 0 .. GC_XF_THREADS - 1
-        // a thread always works on the same 16-byte chunk column and the same row phase (256 threads = 32 rows x 8 chunks per
-        // pass), so the 8 channels it transforms are fixed within a K-block: their coefficients live in registers
-        const int pc = tt & 7, r_base = tt >> 3;
+        // The eight warps work as TWO groups of four on alternate K-blocks: a K-block's transform is a latency chain (coefficients
+        // from L2, box from shared memory, MUFU, stores, the proxy fence: ~1.7 k cycles whatever the arithmetic costs — measured),
+        // so two boxes in flight double the rate. A thread always works on the same 16-byte chunk column and the same row
+        // phase (128 threads = 16 rows x 8 chunks per pass), so the 8 channels it transforms are fixed within a K-block: their
+        // coefficients live in registers.
+        const int xg = tt >> 7, tg = tt & 127;
+        const int pc = tg & 7, r_base = tg >> 3;      // r_base 0..15
         const int lc8 = (pc ^ (r_base & 7)) << 3;     // 128-byte swizzle: logical chunk = physical chunk ^ (row % 8)
-        uint32_t a_slot = 0, a_phase = 0;
+        uint32_t a_slot = xg, a_phase = 0;            // GC_SA is even: group g walks the slots of parity g
         long long dbg_acc[16] = {};
         TC_DBG_T0(tx_all);
-        for (int gi = 0; gi < my_groups; ++gi) {
+        for (int item = xg; item < items; item += 2) {
+            const int gi = item / p.kb_total, kb = item - gi * p.kb_total;
             int tm, n0;
             group_at(gi, tm, n0);
             const bool tile_ok = tm < p.tiles_m;
             const int b = tile_ok ? tm / p.tiles_per_b : 0, t0 = (tm % p.tiles_per_b) * 128;
-            for (int kb = 0; kb < p.kb_total; ++kb) {
+            {
                 // this K-block's coefficients: 64 bytes per thread from L2, requested before the wait for the box
                 const float4* cap = reinterpret_cast<const float4*>(p.coef + static_cast<long long>(b) * p.Cin + kb * 64 + lc8);
                 const float4* cbp = reinterpret_cast<const float4*>(p.coef + (static_cast<long long>(p.B) + b) * p.Cin + kb * 64 + lc8);
@@ -311,16 +318,8 @@ cl_conv3_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_in1, const __grid_c
                 TC_DBG_ACC(7, tw);
                 TC_DBG_T0(tk);
                 uint8_t* col = smem + GcSmem::a + a_slot * GC_A_BYTES + pc * 16 + r_base * 128;
-                // rows r_base + 32 i, i = 0..3 (every thread) and 128 + r_base (r_base < 2 only): all loads first, then the
-                // arithmetic of the four (five) chunks interleaved, then the stores — branch-free, so the MUFU latency of one chunk
-                // hides behind the others. (r % 8) == (r_base % 8) in every pass: the same swizzle phase.
-                uint4 x[4];
-                if (!(kdbg & 16)) {               // ADB_DEBUG timing experiment 16 (results wrong): the transform does nothing
-#pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const uint4*>(col + i * 4096);
-                const bool tail = r_base < GC_A_ROWS - 128;
-                uint4 xt = make_uint4(0u, 0u, 0u, 0u);
-                if (tail) xt = *reinterpret_cast<const uint4*>(col + 4 * 4096);
+                // bf16 in, fp16 out (the MMA's A operand): y = slope x + offset in fp32 (the mean subtraction needs it), then
+                // SiLU(y) = h tanh(h) + h, h = y / 2, on packed fp16 pairs: one MUFU and one HFMA2 per TWO elements
                 auto silu8 = [&](const uint4& xin, bool valid) {
                     const uint32_t xw[4] = {xin.x, xin.y, xin.z, xin.w};
                     uint32_t o[4];
@@ -328,27 +327,41 @@ cl_conv3_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_in1, const __grid_c
                     for (int e = 0; e < 4; ++e) {
                         const float h0 = fmaf(__uint_as_float(xw[e] << 16), av[2 * e], bv[2 * e]);
                         const float h1 = fmaf(__uint_as_float(xw[e] & 0xFFFF0000u), av[2 * e + 1], bv[2 * e + 1]);
-                        // ADB_DEBUG timing experiment 4 (results wrong): no MUFU
-                        const float u0 = (kdbg & 4) ? h0 : tanh_fast(h0), u1 = (kdbg & 4) ? h1 : tanh_fast(h1);
-                        o[e] = valid ? pack_bf16x2(fmaf(h0, u0, h0), fmaf(h1, u1, h1)) : 0u;
+                        const uint32_t hp = pack_f16x2_sat(h0, h1);
+                        const uint32_t tp = (kdbg & 4) ? hp : tanh_f16x2(hp);     // ADB_DEBUG timing experiment 4 (results wrong): no MUFU
+                        o[e] = valid ? hfma2(hp, tp, hp) : 0u;
                     }
                     return make_uint4(o[0], o[1], o[2], o[3]);
                 };
                 const int gr0 = t0 - 1 + r_base;
+                if (!(kdbg & 16)) {               // ADB_DEBUG timing experiment 16 (results wrong): the transform does nothing
+                // rows r_base + 16 i, i = 0..7 (every thread) in two batches of four (loads first, arithmetic interleaved, stores
+                // last: branch-free), then rows 128 + r_base for r_base < 2. (r % 8) == (r_base % 8) in every pass.
 #pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = silu8(x[i], tile_ok && gr0 + 32 * i >= 0 && gr0 + 32 * i < p.L);
-                if (tail) xt = silu8(xt, tile_ok && gr0 + 128 < p.L);
-                if (!(kdbg & 8)) {                // ADB_DEBUG timing experiment 8 (results wrong): no stores
+                for (int hb = 0; hb < 2; ++hb) {
+                    uint4 x[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(col + i * 4096) = x[i];
-                if (tail) *reinterpret_cast<uint4*>(col + 4 * 4096) = xt;
+                    for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const uint4*>(col + (4 * hb + i) * 2048);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int gr = gr0 + 16 * (4 * hb + i);
+                        x[i] = silu8(x[i], tile_ok && gr >= 0 && gr < p.L);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(col + (4 * hb + i) * 2048) = x[i];
+                }
+                if (r_base < GC_A_ROWS - 128) {
+                    uint4 xt = *reinterpret_cast<const uint4*>(col + 8 * 2048);
+                    xt = silu8(xt, tile_ok && gr0 + 128 < p.L);
+                    *reinterpret_cast<uint4*>(col + 8 * 2048) = xt;
                 }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&bar_aready[a_slot], 0);
                 TC_DBG_ACC(8, tk);
-                if (++a_slot == GC_SA) { a_slot = 0; a_phase ^= 1; }
+                a_slot += 2;
+                if (a_slot >= GC_SA) { a_slot -= GC_SA; a_phase ^= 1; }
             }
         }
         TC_DBG_ACC(9, tx_all);

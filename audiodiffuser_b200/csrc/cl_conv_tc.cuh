@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <type_traits>
 #include "ptx.cuh"
 #include "cl_ops.cuh"
 
@@ -347,7 +349,8 @@ __global__ void cl_pack_wavdec_tc_kernel(const float* __restrict__ w, __nv_bfloa
 
 // fp32 [taps][Cin][N] -> bf16 blocks [kb = tap * Cin/64 + cib][N][64] (K-major rows of 128 bytes, what one TMA box
 // with the 128-byte swizzle loads)
-__global__ void cl_pack_conv_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int N, int taps) {
+template <typename OutT>
+__global__ void cl_pack_conv_tc_kernel(const float* __restrict__ w, OutT* __restrict__ out, int Cin, int N, int taps) {
     const long long total = static_cast<long long>(taps) * Cin * N;
     const int kbt = Cin / 64;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -356,7 +359,9 @@ __global__ void cl_pack_conv_tc_kernel(const float* __restrict__ w, __nv_bfloat1
         const int n = static_cast<int>((i >> 6) % N);
         const int kb = static_cast<int>(i / (64LL * N));
         const int tap = kb / kbt, cib = kb % kbt;
-        out[i] = __float2bfloat16_rn(w[(static_cast<long long>(tap) * Cin + cib * 64 + k) * N + n]);
+        const float v = w[(static_cast<long long>(tap) * Cin + cib * 64 + k) * N + n];
+        if constexpr (sizeof(OutT) == 2 && !std::is_same<OutT, __nv_bfloat16>::value) out[i] = __float2half_rn(v);      // fp16 blocks (cl_conv3_gn_tc_kernel)
+        else out[i] = __float2bfloat16_rn(v);
     }
 }
 

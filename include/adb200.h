@@ -233,6 +233,9 @@ int adb_cl_conv(const void* in_dev, const void* w_dev, const float* bias_dev, co
                 int dtype, void* stream);
 int64_t adb_cl_conv_packed_elems(int Cin, int N, int taps);
 int adb_cl_pack_conv_weights(const float* w_f32_dev, void* packed_bf16_dev, int Cin, int N, int taps, void* stream);
+/* the same blocks in fp16: the weight operand of adb_cl_gn_conv3, whose activation operand is produced in fp16 by the fused
+ * GroupNorm / SiLU transform (11 significand bits instead of bf16's 8, and a SiLU that costs one packed MUFU per two elements) */
+int adb_cl_pack_conv_weights_f16(const float* w_f32_dev, void* packed_f16_dev, int Cin, int N, int taps, void* stream);
 /* Weight gradient of the same convolution (what autograd computes for nn.Conv1d weights): out[tap][i][j] (fp32
  * [taps][Ca][Cg], accumulated into) += scale * sum_{b,t} A[b][t + (tap - taps/2)*dil][i] * G[b][t][j], rows of A
  * outside [0, L) read as zero. ADB_DTYPE_BF16: tcgen05 with MN-major operands straight from the channels-last tensors. */
@@ -275,7 +278,7 @@ int adb_cl_gn_coef(const void* in_dev, double* sums_dev, int* tickets_dev, float
 /* Second half: out = bias + res + Conv1d_k3_same(SiLU(slope * x + offset)) with the activation applied inside the convolution's
  * operand path, so the normalised tensor (and the concatenation) never exists in HBM (unet1d.py:186-193, the residual add of
  * ResnetBlock1d :315). x = in1_dev [B][L][C1], or the channel concatenation [in1 | in2] (in2_dev [B][L][C2], NULL / 0 for one
- * input); coef_dev from adb_cl_gn_coef over C1 + C2 channels; w_packed_dev from adb_cl_pack_conv_weights(C1 + C2, N, 3). */
+ * input); coef_dev from adb_cl_gn_coef over C1 + C2 channels; w_packed_dev from adb_cl_pack_conv_weights_f16(C1 + C2, N, 3). */
 int adb_cl_gn_conv3(const void* in1_dev, int C1, const void* in2_dev, int C2, const float* coef_dev, const void* w_packed_dev,
                     const float* bias_dev, const void* res_dev, void* out_dev, int B, int L, int N, void* stream);
 /* adb_cl_conv (bf16, plain store) over the channel concatenation of two inputs that is never materialised: K-blocks of the first

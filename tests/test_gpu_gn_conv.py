@@ -1,8 +1,9 @@
 """GPU parity of the fused GroupNorm-apply convolution (adb_cl_gn_conv3, ConvBlock1d of unet1d.py:160-207 with the channel
 concatenation of UpsampleBlock1d :552-556 folded in) and of the two-input plain convolution (adb_cl_conv_cat):
 
-  * against the unfused C-ABI sequence adb_cl_concat -> adb_cl_groupnorm -> adb_cl_conv on the same bf16 inputs (same
-    arithmetic for the normalisation, so the difference is the fp32 accumulation order and one rounding of the scaled skip),
+  * against the unfused C-ABI sequence adb_cl_concat -> adb_cl_groupnorm -> adb_cl_conv on the same bf16 inputs (the fused kernel
+    feeds the tensor core fp16 operands — normalised activations and weights with 11 significand bits — where the unfused path
+    rounds both to bf16, so it is the more accurate of the two),
   * against torch's group_norm / silu / conv1d evaluated in fp64 on the same bf16-rounded inputs.
 """
 import math
@@ -48,6 +49,8 @@ def test_gn_conv3_vs_unfused_and_fp64(dev, B, L, C1, C2, N, cond, res):
     r = rnd(B, L, N).to(dev).to(torch.bfloat16) if res else None
     packed = torch.empty(lib.adb_cl_conv_packed_elems(Cin, N, 3), dtype=torch.bfloat16, device=dev)
     Nn.check(lib.adb_cl_pack_conv_weights(Nn.ptr(w), Nn.ptr(packed), Cin, N, 3, st))
+    packed16 = torch.empty(lib.adb_cl_conv_packed_elems(Cin, N, 3), dtype=torch.float16, device=dev)     # the fused kernel's fp16 operand
+    Nn.check(lib.adb_cl_pack_conv_weights_f16(Nn.ptr(w), Nn.ptr(packed16), Cin, N, 3, st))
 
     # fused: statistics + coefficients of the raw inputs, then one kernel
     sums = torch.zeros(B * G * 2, dtype=torch.float64, device=dev)
@@ -64,7 +67,7 @@ def test_gn_conv3_vs_unfused_and_fp64(dev, B, L, C1, C2, N, cond, res):
             Nn.check(lib.adb_cl_gn_coef(Nn.ptr(sk), Nn.ptr(sums), Nn.ptr(tickets), Nn.ptr(coef), B, L, C2, G - g1, G, g1, C1, Cin,
                                         Nn.ptr(gamma), Nn.ptr(beta), Nn.ptr(ss), ss_ld, eps, s2, st))
         out.zero_()
-        Nn.check(lib.adb_cl_gn_conv3(Nn.ptr(h), C1, Nn.ptr(sk), C2, Nn.ptr(coef), Nn.ptr(packed), Nn.ptr(bias), Nn.ptr(r), Nn.ptr(out),
+        Nn.check(lib.adb_cl_gn_conv3(Nn.ptr(h), C1, Nn.ptr(sk), C2, Nn.ptr(coef), Nn.ptr(packed16), Nn.ptr(bias), Nn.ptr(r), Nn.ptr(out),
                                      B, L, N, st))
         Nn.check_async()
         assert float(sums.abs().max()) == 0.0 and int(tickets.abs().max()) == 0
@@ -89,8 +92,7 @@ def test_gn_conv3_vs_unfused_and_fp64(dev, B, L, C1, C2, N, cond, res):
     if cond:
         y = y * (ss[:, :Cin].double().unsqueeze(2) + 1) + ss[:, Cin:2 * Cin].double().unsqueeze(2)
     y = F.silu(y)
-    wb = w.to(torch.bfloat16).double()
-    want = F.conv1d(y, wb.permute(2, 1, 0), bias.double(), padding=1).transpose(1, 2)
+    want = F.conv1d(y, w.double().permute(2, 1, 0), bias.double(), padding=1).transpose(1, 2)     # unrounded weights: the two paths round them differently
     if res:
         want = want + r.double()
 

@@ -25,6 +25,8 @@ for (L, C1, C2, Nn, res) in [(4096, 256, 0, 256, False), (4096, 256, 0, 256, Tru
     r = torch.randn(B, L, Nn, device=dev).to(torch.bfloat16) if res else None
     packed = torch.empty(lib.adb_cl_conv_packed_elems(Cin, Nn, 3), dtype=torch.bfloat16, device=dev)
     N.check(lib.adb_cl_pack_conv_weights(N.ptr(w), N.ptr(packed), Cin, Nn, 3, st))
+    packed16 = torch.empty(lib.adb_cl_conv_packed_elems(Cin, Nn, 3), dtype=torch.float16, device=dev)
+    N.check(lib.adb_cl_pack_conv_weights_f16(N.ptr(w), N.ptr(packed16), Cin, Nn, 3, st))
     sums = torch.zeros(B * G * 2, dtype=torch.float64, device=dev)
     tickets = torch.zeros(B, dtype=torch.int32, device=dev)
     coef = torch.empty(2, B, Cin, dtype=torch.float32, device=dev)
@@ -38,7 +40,7 @@ for (L, C1, C2, Nn, res) in [(4096, 256, 0, 256, False), (4096, 256, 0, 256, Tru
     stats()
     out = torch.empty(B, L, Nn, dtype=torch.bfloat16, device=dev)
     def fused():
-        N.check(lib.adb_cl_gn_conv3(N.ptr(h), C1, N.ptr(sk), C2, N.ptr(coef), N.ptr(packed), N.ptr(bias), N.ptr(r), N.ptr(out), B, L, Nn, st))
+        N.check(lib.adb_cl_gn_conv3(N.ptr(h), C1, N.ptr(sk), C2, N.ptr(coef), N.ptr(packed16), N.ptr(bias), N.ptr(r), N.ptr(out), B, L, Nn, st))
     cat = torch.cat([h, sk], dim=2).contiguous() if C2 else h
     def plain():
         N.check(lib.adb_cl_conv(N.ptr(cat), N.ptr(packed), N.ptr(bias), N.ptr(r), N.ptr(out), B, L, L, Cin, Nn, 3, -1, 1, 0, 0, 0, 0, 1, st))
