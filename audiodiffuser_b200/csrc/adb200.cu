@@ -411,6 +411,8 @@ struct adb_wavenet {
     int block_kernel = 3;
     int zs_pipe = 1;                            // z-stash kernel: software-pipelined job order (ADB_ZS_PIPE=0: plain per-group order)
     int zs_hi_roles = 0;                        // z-stash kernel: producer / MMA issuer on the highest warp ids (ADB_ZS_HI_ROLES)
+    int zs_ml_S = 0;                            // > 0: ONE wavefront launch for all blocks of a chunk, sub-passes of this many samples
+                                                // kept L2-resident across the blocks (ADB_ZS_ML; 0 = one launch per block)
     int pair = 1;                               // derived: block_kernel != 0
     int no_stash = 0;                           // derived: block_kernel == 1
     int chunk = 256;                            // samples per pass of the bf16 stack (ADB_CHUNK): bounds the workspace
@@ -752,6 +754,11 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             if (pe) n->zs_pipe = atoi(pe) != 0;
             const char* he = getenv("ADB_ZS_HI_ROLES");
             if (he) n->zs_hi_roles = atoi(he) != 0;
+            const char* me = getenv("ADB_ZS_ML");
+            if (me && atoi(me) >= 0) n->zs_ml_S = atoi(me);
+            // the wavefront needs a block's tiles to complete within ~1.5 tile times of their first load: the software-pipelined job
+            // order keeps two groups in flight per pair and would make the pairs wait on each other
+            if (n->zs_ml_S > 0 && !pe) n->zs_pipe = 0;
             const char* fe = getenv("ADB_FUSE_TAIL");
             if (fe) n->fuse_tail = atoi(fe) != 0;
             const char* ce = getenv("ADB_CHUNK");
@@ -767,8 +774,10 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         CKN(cudaFuncSetAttribute(wavenet_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_BLOCK_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TAIL_SMEM_BYTES));
-        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
-        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+        CKN(cudaFuncSetAttribute(wavenet_block_zs_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_skip_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_GEMM_SMEM_BYTES));
         CKN(cudaFuncSetAttribute(wavenet_skip_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKIP_TAIL_SMEM_BYTES));
     }
@@ -827,6 +836,7 @@ struct Workspace {
     // z-stash kernel: [G][Bc][L][C] fp16 bits, the gated activations of G consecutive blocks (skip GEMM operand);
     // pair kernel: [Bc][L][C] fp16 bits, an even block's skip term consumed by the next block
     __nv_bfloat16* stash;
+    unsigned int* ml_flags;              // multi-layer block launch: [layers][Bc * tiles] completion counters
     int Bc, G;
     int64_t total;
 };
@@ -880,6 +890,8 @@ static Workspace carve(const adb_wavenet* n, int B, int L, int precision, void* 
         w.hbA = reinterpret_cast<__nv_bfloat16*>(take(BcL * C * 2));
         w.hbB = reinterpret_cast<__nv_bfloat16*>(take(BcL * C * 2));
         w.stash = reinterpret_cast<__nv_bfloat16*>(take(BcL * C * 2 * w.G));
+        if (zs && n->zs_ml_S > 0)
+            w.ml_flags = reinterpret_cast<unsigned int*>(take(static_cast<int64_t>(n->layers) * w.Bc * ((L + TC_TILE_T - 1) / TC_TILE_T) * 4));
     }
     w.total = off;
     return w;
@@ -982,15 +994,44 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
         if (!rc) rc = get_act_map(n, w.skip, bc, L, 2, &m_skip);
         if (rc) return rc;
         __nv_bfloat16 *hin = h_save ? h_save : w.hbA, *hout = (h_save && layers > 1) ? h_save + BL * C : w.hbB;
+        const bool ml = n->zs_ml_S > 0 && !h_save && w.G == layers && w.ml_flags != nullptr && layers > 1;
+        if (ml) {
+            // all blocks of this chunk in ONE wavefront launch (wavenet_tc3.cuh, ML = true)
+            ScopedTimer t(n, ADB_TIMER_CONV, st, layers);
+            CUtensorMap m_hA, m_hB, m_hAo, m_hBo;
+            rc = get_act_map(n, w.hbA, bc, L, 0, &m_hA);
+            if (!rc) rc = get_act_map(n, w.hbB, bc, L, 0, &m_hB);
+            if (!rc) rc = get_act_map(n, w.hbA, bc, L, 4, &m_hAo);
+            if (!rc) rc = get_act_map(n, w.hbB, bc, L, 4, &m_hBo);
+            if (rc) return rc;
+            CK(cudaMemsetAsync(w.ml_flags, 0, sizeof(unsigned int) * layers * num_tiles, st));
+            BlockZsParams bp;
+            memset(&bp, 0, sizeof bp);
+            bp.E = w.E; bp.b2 = nullptr; bp.h_in = w.hbA; bp.h_in2 = w.hbB; bp.h_out_dbg = nullptr; bp.y_out = nullptr;
+            bp.B = bc; bp.L = L; bp.layer = 0; bp.layers = layers; bp.dil = 1;
+            bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
+            bp.write_h = 1;                       // uniform job structure; the last block's h' stores are skipped in the kernel
+            bp.zrow0 = 0; bp.hi_roles = n->zs_hi_roles; bp.dbg = n->dbg;
+            bp.b2_tab = n->d_b2; bp.ml_flags = w.ml_flags; bp.cycle = n->cycle;
+            bp.ml_S = n->zs_ml_S < bc ? n->zs_ml_S : bc;
+            const int full_sp = bc / bp.ml_S, rem = bc % bp.ml_S;
+            bp.ml_items_per_sp = layers * ((bp.ml_S * tiles_per_b + 1) / 2);
+            bp.ml_items = full_sp * bp.ml_items_per_sp + layers * ((rem * tiles_per_b + 1) / 2);
+            lc.dynamicSmemBytes = TC3_SMEM_BYTES;
+            // even blocks read ping (hbA) and write pong (hbB), odd blocks the other way round
+            if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
+            else            CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
+        }
         for (int l = 0; l < layers; ++l) {
             const int slot = l % w.G;
-            {
+            if (!ml) {
                 ScopedTimer t(n, ADB_TIMER_CONV, st);
                 CUtensorMap m_h, m_hout;
                 rc = get_act_map(n, hin, bc, L, 0, &m_h);
                 if (!rc) rc = get_act_map(n, hout, bc, L, 4, &m_hout);
                 if (rc) return rc;
                 BlockZsParams bp;
+                memset(&bp, 0, sizeof bp);
                 bp.E = w.E; bp.b2 = n->L[l].b2; bp.h_in = hin; bp.h_out_dbg = hout;
                 bp.y_out = y_save ? y_save + static_cast<long long>(l) * BL * 2 * C : nullptr;
                 bp.B = bc; bp.L = L; bp.layer = l; bp.layers = layers; bp.dil = 1 << (l % n->cycle);
@@ -1000,8 +1041,8 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 bp.hi_roles = n->zs_hi_roles;
                 bp.dbg = n->dbg;
                 lc.dynamicSmemBytes = TC3_SMEM_BYTES;
-                if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true>, m_h, n->tm_w2, m_hout, m_zst, bp));
-                else            CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false>, m_h, n->tm_w2, m_hout, m_zst, bp));
+                if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true, false>, m_h, n->tm_w2, m_hout, m_zst, m_h, m_hout, bp));
+                else            CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false, false>, m_h, n->tm_w2, m_hout, m_zst, m_h, m_hout, bp));
             }
             if (h_save) { hin = hout; hout = (l + 2 < layers) ? hin + BL * C : w.hbB; }
             else { __nv_bfloat16* tmp = hin; hin = hout; hout = tmp; }

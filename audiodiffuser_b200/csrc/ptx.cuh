@@ -367,6 +367,20 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
+// the same load served at L2 (no L1 allocation / hit): for data other CTAs wrote earlier in the same launch
+__device__ __forceinline__ void ldg256_cg(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// orders generic-proxy and async-proxy (TMA) accesses of this thread in both directions, all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
                  "r"(r[5]), "r"(r[6]), "r"(r[7])

@@ -97,7 +97,7 @@ __device__ unsigned long long g_tc_cycles[16];
 
 enum TcWaitSite : uint32_t {
     SITE_PROD_EMPTY = 1, SITE_MMA_TEMPTY = 2, SITE_MMA_ZREADY = 3, SITE_MMA_FULL = 4, SITE_EPI_TFULL = 5,
-    SITE_TAIL_W = 6, SITE_TAIL_MMA = 7,
+    SITE_TAIL_W = 6, SITE_TAIL_MMA = 7, SITE_ML_FLAG = 8,
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

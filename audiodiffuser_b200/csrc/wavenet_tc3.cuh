@@ -57,6 +57,13 @@ struct BlockZsParams {
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
     int zrow0;                      // first "batch" coordinate of this layer's slot in the stash map (slot * B)
     int hi_roles;                   // 1: producer / MMA issuer on warps 8 / 9 (highest scheduler priority), epilogue on 0..7
+    // multi-layer launch (ML = true): all blocks of the chunk in wavefront order
+    const __nv_bfloat16* h_in2;     // pong buffer (residual input of odd layers)
+    const float* const* b2_tab;     // per-layer output-projection biases
+    unsigned int* ml_flags;         // [layers][num_tiles] completion counters of the h' stores (zero at launch; a tile is done at 8)
+    int cycle;                      // dilation = 1 << (layer % cycle)
+    int ml_S;                       // samples per sub-pass
+    int ml_items, ml_items_per_sp;  // (sub-pass, layer, group) items of the launch / of one full sub-pass
     int dbg;                        // ADB_DEBUG builds only: 2 = in-kernel cycle accounting; timing experiments (results wrong):
                                     // 4 no A re-load for G1b, 8 no stash stores, 16 no h' stores, 32 no gate math, 64 no residual read,
                                     // 1024 all stores to a fixed L2-resident tile per CTA
@@ -85,10 +92,17 @@ __host__ __device__ __forceinline__ bool zs_job_at(int s, int n, int write_h, in
     return i < n;
 }
 
-template <bool PIPE>
+// ML = true: ONE launch runs ALL blocks of a 256-sample chunk as a wavefront over (sub-pass of S samples, layer, tile group): block
+// l + 1 of a tile starts as soon as block l has written the +-d neighbourhood it reads (per-tile completion flags in global
+// memory; the groups are dealt to the CTA pairs round-robin in wavefront order, so a pair only ever waits for EARLIER items and
+// all pairs are co-resident: no deadlock). With S = 2..4 the residual stream of a sub-pass (ping + pong, 2 x S x 8.2 MB) stays in
+// L2 across the 36 blocks: h is read from and h' overwritten in L2, only the z stash streams to HBM. Layer l reads ping for even
+// l and pong for odd l (tm_h / tm_h2, p.h_in / p.h_in2) and writes the other (tm_hout / tm_hout2).
+template <bool PIPE, bool ML>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_hout, const __grid_constant__ CUtensorMap tm_zst,
+                        const __grid_constant__ CUtensorMap tm_h2, const __grid_constant__ CUtensorMap tm_hout2,
                         const BlockZsParams p) {
     TC_DBG_FLAGS(p);
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -139,9 +153,26 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
 
     const int pair_id = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
-    const int num_groups = (p.num_tiles + 1) >> 1;
+    const int num_groups = ML ? p.ml_items : (p.num_tiles + 1) >> 1;           // ML: (sub-pass, layer, group) items in wavefront order
     const int n_mine = (num_groups - pair_id + num_pairs - 1) / num_pairs;     // tile groups of this CTA pair (>= 1)
     const int n_slots = zs_num_slots<PIPE>(n_mine, p.write_h);
+    // this CTA's tile of the pair's gi-th group, and (ML) the block it belongs to
+    auto item_at = [&](int gi, int& layer, int& tile, bool& valid) {
+        if constexpr (!ML) {
+            layer = p.layer;
+            tile = (pair_id + gi * num_pairs) * 2 + rank;
+            valid = tile < p.num_tiles;
+        } else {
+            const int n = pair_id + gi * num_pairs;
+            const int sp = n / p.ml_items_per_sp, r = n - sp * p.ml_items_per_sp;
+            const int t_begin = sp * p.ml_S * p.tiles_per_b;
+            const int t_end = min(p.num_tiles, t_begin + p.ml_S * p.tiles_per_b);
+            const int groups = (t_end - t_begin + 1) >> 1;
+            layer = r / groups;
+            tile = t_begin + 2 * (r - layer * groups) + rank;
+            valid = tile < t_end;
+        }
+    };
 
     if (warp == w_prod) {
         // ===================== TMA producer (both CTAs) =====================
@@ -151,10 +182,42 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         for (int s = 0; s < n_slots; ++s) {
             int job, gi;
             if (!zs_job_at<PIPE>(s, n_mine, p.write_h, job, gi)) continue;
-            const int tile = (pair_id + gi * num_pairs) * 2 + rank;
-            const int b = tile / p.tiles_per_b;           // >= B for a padding tile: TMA zero-fills
+            int layer, tile;
+            bool tvalid;
+            item_at(gi, layer, tile, tvalid);
+            const int b = tvalid ? tile / p.tiles_per_b : p.B;      // >= B for a padding tile: TMA zero-fills
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
+            const int dil = ML ? 1 << (layer % p.cycle) : p.dil;
             const int nkb = job < 2 ? 12 : 4;
+            if (ML && job == 0 && layer > 0 && tvalid) {
+                // wavefront dependency: the previous block must have finished every tile this one reads (+-dil rows) and every tile whose
+                // readers this one's h' store would overrun (+-previous dilation: ping / pong are reused every second block)
+                const int dprev = 1 << ((layer - 1) % p.cycle);
+                const int dmax = dil > dprev ? dil : dprev;
+                const int kt = (dmax + TC_TILE_T - 1) / TC_TILE_T;
+                const int tb0 = b * p.tiles_per_b, tb1 = tb0 + p.tiles_per_b - 1;
+                const int lo = max(tile - kt, tb0), hi = min(tile + kt, tb1);
+                const unsigned int* fl = p.ml_flags + static_cast<long long>(layer - 1) * p.num_tiles;
+                TC_DBG_T0(tf);
+                for (int j = lo + lane; j <= hi; j += 32) {
+                    unsigned int polls = 0;
+                    while (ld_acquire_gpu_u32(fl + j) < TC_EPI_THREADS / 32) {
+                        __nanosleep(64);
+                        if ((++polls & 0xFFF) == 0 && *reinterpret_cast<volatile unsigned int*>(&g_spin_guard.abort_flag) != 0) break;
+                        if (polls > (1u << 24)) {               // ~2 s: give up loudly instead of hanging the GPU
+                            if (atomicCAS(&g_spin_guard.abort_flag, 0u, 1u) == 0u) {
+                                g_spin_guard.site = SITE_ML_FLAG; g_spin_guard.block = blockIdx.x; g_spin_guard.aux = layer;
+                                __threadfence();
+                            }
+                            break;
+                        }
+                    }
+                }
+                __syncwarp();
+                fence_proxy_async_all();            // the neighbours' TMA stores (async proxy) before this CTA's TMA loads
+                TC_DBG_ACC(7, tf);
+            }
+            const CUtensorMap* tmh = (ML && (layer & 1)) ? &tm_h2 : &tm_h;
             for (int kb = 0; kb < nkb; ++kb) {
                 TC_DBG_T0(tw);
                 mbar_wait(&bar_empty[stage], phase ^ 1, SITE_PROD_EMPTY, stage);
@@ -162,7 +225,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 if (lane == 0) {
                     uint8_t* sa = smem + Tc3Smem::stages + stage * T3_STAGE_BYTES;
                     uint8_t* sb = sa + T3_A_BYTES;
-                    const int wblk = p.layer * TC_W_BLOCKS_PER_LAYER + (job < 2 ? job * 12 + kb : 24 + kb);
+                    const int wblk = layer * TC_W_BLOCKS_PER_LAYER + (job < 2 ? job * 12 + kb : 24 + kb);
                     const bool load_a = job < 2 && !((kdbg & 4) && job == 1);     // timing experiment: G1b re-uses stale A tiles
                     const uint32_t bytes = load_a ? T3_STAGE_BYTES : T3_B_BYTES;
                     if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * bytes);   // both CTAs' bytes
@@ -171,7 +234,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                         const int tap = kb >> 2, cib = kb & 3;
                         // 2048 (timing experiment): activations confined to a window of (dbg >> 16) samples, i.e. L2-resident
                         const int lb = (kdbg & 2048) ? b % (kdbg >> 16) : b;
-                        tma_load_3d_pair(sa, &tm_h, &bar_full[stage], cib * 64, t0 + (tap - 1) * p.dil, lb);
+                        tma_load_3d_pair(sa, tmh, &bar_full[stage], cib * 64, t0 + (tap - 1) * dil, lb);
                     }
                     tma_load_2d_pair(sb, &tm_w, &bar_full[stage], 0, wblk * 256 + rank * 128);
                 }
@@ -180,7 +243,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             }
         }
         TC_DBG_ACC(6, tp_all);
-        if ((kdbg & 2) && lane == 0 && leader) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); }
+        if ((kdbg & 2) && lane == 0 && leader) { atomicAdd(&g_tc_cycles[5], dbg_acc[5]); atomicAdd(&g_tc_cycles[6], dbg_acc[6]); atomicAdd(&g_tc_cycles[12], dbg_acc[7]); }
     } else if (warp == w_mma) {
         if (leader) {
             // ===================== MMA issuer (rank 0 only) =====================
@@ -250,18 +313,31 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         uint8_t* own0 = zbase + half * TC_A_BYTES + q * 4096;
         uint8_t* own1 = zbase + (2 + half) * TC_A_BYTES + q * 4096;
         uint8_t* tbuf = smem + Tc3Smem::stg + ew * T3_STG_BYTES;
-        const float* b2g = p.b2 + half * 128;
         uint32_t jg = 0;
+        int flag_tile = -1, flag_layer = 0;   // ML: tile whose h' stores are in flight; its completion flag is raised once they have landed
+        // raise the pending completion flag: this warp's h' stores (and everything else it committed) are performed, then one
+        // release-add per warp; a tile is complete when its 8 epilogue warps have added
+        auto raise_flag = [&]() {
+            if (ML && flag_tile >= 0) {
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    fence_proxy_async_all();
+                    __threadfence();
+                    atomicAdd(p.ml_flags + static_cast<long long>(flag_layer) * p.num_tiles + flag_tile, 1u);
+                }
+                flag_tile = -1;
+            }
+        };
         uint32_t zp[2][16];                   // gated activations of a G1a job whose z write waits for the previous G2r (PIPE)
         bool z_pending = false;
-        int pend_t0 = 0, pend_b = 0;
+        int pend_t0 = 0, pend_b = 0, pend_zrow = 0;
         bool pend_valid = false;
         long long dbg_acc[12] = {};
         TC_DBG_T0(te_all);
 
         // write this warp's 32 x 64-channel piece of z (from zp) into K-block 2 j + half, publish it to the MMA issuer and send it
         // to the stash
-        auto publish_z = [&](int j, int zt0, int zb, bool zvalid) {
+        auto publish_z = [&](int j, int zt0, int zb, bool zvalid, int zrow0) {
             uint8_t* own = j ? own1 : own0;
             if (lane == 0) tma_store_wait_read<0>();      // the previous stash store from these bytes has been read
             __syncwarp();
@@ -281,7 +357,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                     // 1024 (timing experiment): every CTA stores to its own fixed tile, so the stores never leave L2
                     const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : zt0;
                     const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : zb;
-                    tma_store_3d(&tm_zst, own, (2 * j + half) * 64, st0 + q * 32, p.zrow0 + sb);
+                    tma_store_3d(&tm_zst, own, (2 * j + half) * 64, st0 + q * 32, zrow0 + sb);
                     tma_store_commit();
                 }
             }
@@ -291,17 +367,20 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
         for (int s = 0; s < n_slots; ++s) {
             int job, gi;
             if (!zs_job_at<PIPE>(s, n_mine, p.write_h, job, gi)) continue;
-            const int tile = (pair_id + gi * num_pairs) * 2 + rank;
-            const bool tile_valid = tile < p.num_tiles;
+            int layer, tile;
+            bool tile_valid;
+            item_at(gi, layer, tile, tile_valid);
             const int b = tile / p.tiles_per_b;
             const int t0 = (tile % p.tiles_per_b) * TC_TILE_T;
             const int t = t0 + row;
+            const int dil = ML ? 1 << (layer % p.cycle) : p.dil;
+            const int zrow0 = ML ? layer * p.B : p.zrow0;
             const uint32_t buf = jg & 1;
             const uint32_t par = (jg >> 1) & 1;
             ++jg;
             if (job < 2) {
                 // ---- epilogue 1: gate ----
-                const float* Eg = p.E + (static_cast<long long>(tile_valid ? b : 0) * p.layers + p.layer) * 1536;
+                const float* Eg = p.E + (static_cast<long long>(tile_valid ? b : 0) * p.layers + layer) * 1536;
                 if (job == 0) {
                     // interior tiles (every row sees all three taps) add ONE vector: E0 + E1 + E2, gate half pre-scaled by 1/2
                     named_bar_sync(1, TC_EPI_THREADS);            // everyone is done with the previous group's vector
@@ -309,10 +388,11 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                         s_esum[i] = (Eg[i] + Eg[512 + i] + Eg[1024 + i]) * (i < 256 ? 0.5f : 1.0f);
                     named_bar_sync(1, TC_EPI_THREADS);
                 }
-                const float m_lo = (t >= p.dil) ? 1.0f : 0.0f;
-                const float m_hi = (t < p.L - p.dil) ? 1.0f : 0.0f;
-                const bool interior = (t0 >= p.dil) && (t0 + TC_TILE_T - 1 < p.L - p.dil);
+                const float m_lo = (t >= dil) ? 1.0f : 0.0f;
+                const float m_hi = (t < p.L - dil) ? 1.0f : 0.0f;
+                const bool interior = (t0 >= dil) && (t0 + TC_TILE_T - 1 < p.L - dil);
                 const int j = job;
+                raise_flag();                  // the previous group's h' stores have had an MMA job's time to land
                 TC_DBG_T0(tw);
                 mbar_wait(&bar_tfull[buf], par, SITE_EPI_TFULL, j);
                 TC_DBG_ACC(7, tw);
@@ -385,9 +465,9 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 // (pipelined order): keep the values in registers until its accumulator-ready event, which is next in line.
                 // G1b is always issued after the previous G2r, so its completion already implies that z is free.
                 if (PIPE && p.write_h && j == 0 && gi > 0) {
-                    z_pending = true; pend_t0 = t0; pend_b = b; pend_valid = tile_valid;
+                    z_pending = true; pend_t0 = t0; pend_b = b; pend_valid = tile_valid; pend_zrow = zrow0;
                 } else {
-                    publish_z(j, t0, b, tile_valid);
+                    publish_z(j, t0, b, tile_valid, zrow0);
                 }
                 TC_DBG_ACC(8, tk);
             } else {
@@ -397,13 +477,19 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 {
                     const bool ok = tile_valid && t < p.L && !(kdbg & 64);     // 64: timing experiment without the residual read
                     const int rb = (kdbg & 2048) ? b % (kdbg >> 16) : b;
-                    const __nv_bfloat16* hrow = p.h_in + (static_cast<long long>(ok ? rb : 0) * p.L + (ok ? t : 0)) * TC_C + half * 128;
+                    const __nv_bfloat16* hsrc = (ML && (layer & 1)) ? p.h_in2 : p.h_in;
+                    const __nv_bfloat16* hrow = hsrc + (static_cast<long long>(ok ? rb : 0) * p.L + (ok ? t : 0)) * TC_C + half * 128;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         if (ok) {
                             uint32_t lo[8], hi[8];
-                            ldg256(hrow + cc * 32, lo);
-                            ldg256(hrow + cc * 32 + 16, hi);
+                            if constexpr (ML) {       // written by other CTAs earlier in this launch: read at L2, never from a stale L1 line
+                                ldg256_cg(hrow + cc * 32, lo);
+                                ldg256_cg(hrow + cc * 32 + 16, hi);
+                            } else {
+                                ldg256(hrow + cc * 32, lo);
+                                ldg256(hrow + cc * 32 + 16, hi);
+                            }
 #pragma unroll
                             for (int i = 0; i < 8; ++i) { hres[cc][i] = lo[i]; hres[cc][8 + i] = hi[i]; }
                         } else {
@@ -418,9 +504,12 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 TC_DBG_T0(tk3);
                 tc_fence_after_sync();
                 if (z_pending) {              // this G2r has finished reading z: the next group's K-blocks 0,1 can land
-                    publish_z(0, pend_t0, pend_b, pend_valid);
+                    publish_z(0, pend_t0, pend_b, pend_valid, pend_zrow);
                     z_pending = false;
                 }
+                const float* b2g = (ML ? p.b2_tab[layer] : p.b2) + half * 128;
+                const bool store_h = !ML || layer + 1 < p.layers;        // the last block's residual output is never used
+                const CUtensorMap* tmo = (ML && (layer & 1)) ? &tm_hout2 : &tm_hout;
                 const int sw_w = (lane >> 1) & 3;                 // write swizzle of this lane's own row
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
@@ -449,22 +538,24 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                         *reinterpret_cast<uint4*>(box + lane * 64 + ((m ^ sw_w) << 4)) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && tile_valid && !(kdbg & 16)) {
+                    if (lane == 0 && tile_valid && store_h && !(kdbg & 16)) {
                         const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : t0;
                         const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : (kdbg & 2048) ? b % (kdbg >> 16) : b;
-                        tma_store_3d(&tm_hout, box, col, st0 + q * 32, sb);
+                        tma_store_3d(tmo, box, col, st0 + q * 32, sb);
                         tma_store_commit();
                     }
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&bar_tempty[buf], 0);
+                if (ML && tile_valid && store_h) { flag_tile = tile; flag_layer = layer; }
                 TC_DBG_ACC(10, tk3);
             }
         }
         TC_DBG_ACC(11, te_all);
         if ((kdbg & 2) && ew == 0 && lane == 0 && leader)
             for (int i = 7; i < 12; ++i) atomicAdd(&g_tc_cycles[i], dbg_acc[i]);
+        raise_flag();
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores fully performed before exit
     }
 

@@ -272,6 +272,27 @@ def test_zstash_passes_and_layer_groups(dev, monkeypatch, chunk, stash_gb):
         assert torch.equal(out, base)                                  # passes alone do not change a single bit
 
 
+@pytest.mark.parametrize("S,pipe", [(1, 0), (2, 0), (2, 1), (5, 1)])
+def test_multilayer_wavefront_launch_is_bit_identical(dev, monkeypatch, S, pipe):
+    """ADB_ZS_ML = S (opt-in): all blocks of a chunk in ONE launch as a wavefront over (sub-pass of S samples, layer,
+    tile group) with per-tile completion flags, ping / pong reused in L2. Same arithmetic per tile, so the waveforms must be
+    bit-identical to the one-launch-per-block path — for any sub-pass size, including a ragged last sub-pass and a dilation
+    (2048) that reaches across 16 tiles, and with either job order."""
+    from audiodiffuser_b200 import _native as N
+    g = load_golden("wavenet_c256_l13_dil2048")
+    C, layers, cycle, B, L, seed = (int(v) for v in g["cfg"])
+    audio, t = torch.from_numpy(g["audio"]).to(dev), torch.from_numpy(g["t"]).to(dev)
+    x = torch.cat([audio, audio.flip(0), audio[:1]], 0).contiguous()       # batch 2 B + 1: ragged sub-passes
+    tt = torch.cat([t, t.flip(0), t[:1]], 0).contiguous()
+    base = make_net(C, layers, cycle, seed, "bf16", dev)(x, tt)
+    monkeypatch.setenv("ADB_ZS_ML", str(S))
+    monkeypatch.setenv("ADB_ZS_PIPE", str(pipe))
+    out = make_net(C, layers, cycle, seed, "bf16", dev)(x, tt)
+    N.check_async()
+    assert torch.equal(out, base)
+    assert rel_l2(out[:B], g["out"]) < TOL["bf16"]
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_forward_debug_per_block_outputs_vs_oracle(dev, precision):
     """adb_wavenet_forward_debug: the residual stream h and the running skip sum after every block against the oracle's

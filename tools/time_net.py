@@ -46,7 +46,7 @@ if os.environ.get("ADB_DEBUG_FLAGS") and int(os.environ["ADB_DEBUG_FLAGS"]) & 2:
     net(x, t)
     lib.adb_debug_tc_cycles(buf, 1)
     names = ["mma:wait tempty(G1)", "mma:wait tempty(G2)", "mma:wait zready", "mma:wait full", "mma:total", "prod:wait empty",
-             "prod:total", "epi:wait tfull(G1)", "epi:E1 work", "epi:wait tfull(G2)", "epi:E2 work", "epi:total"]
+             "prod:total", "epi:wait tfull(G1)", "epi:E1 work", "epi:wait tfull(G2)", "epi:E2 work", "epi:total", "prod:wait flags (ML)"]
     ntiles = B * 125 * layers
     for i, n in enumerate(names):
         print(f"  {n:24s} {buf[i] / ntiles:10.0f} cycles/tile")
