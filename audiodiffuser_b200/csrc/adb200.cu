@@ -1019,8 +1019,13 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
             bp.ml_items = full_sp * bp.ml_items_per_sp + layers * ((rem * tiles_per_b + 1) / 2);
             lc.dynamicSmemBytes = TC3_SMEM_BYTES;
             // even blocks read ping (hbA) and write pong (hbB), odd blocks the other way round
-            if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
-            else            CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
+            // The pipelined order issues G1a of a pair's NEXT item before G2r of the current one: the next item's dependency wait then
+            // sits in front of the current item's last job. That is only safe while the next item (pairs items later) cannot depend,
+            // directly or transitively, on the current one, i.e. while a layer of a sub-pass has more groups than pairs + the widest
+            // neighbourhood (17 tiles); otherwise the plain order, whose waits only ever precede an item's own jobs.
+            const bool use_pipe = n->zs_pipe && (bp.ml_S * tiles_per_b + 1) / 2 > pairs + 17;
+            if (use_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
+            else          CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
         }
         for (int l = 0; l < layers; ++l) {
             const int slot = l % w.G;
