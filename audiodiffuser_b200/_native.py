@@ -92,7 +92,8 @@ _SIGS = {
     "adb_cl_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_cl_concat": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "adb_cl_wavenc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "adb_cl_wavenc_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_wavenc_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "adb_edm_precond_coef": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "adb_cl_wavdec": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "adb_wavenet_train_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int]),
     "adb_wavenet_dsm_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int,

@@ -339,7 +339,10 @@ class UNet1dBase(nn.Module):
         return P
 
     # ---- one forward as a sequence of C-ABI calls -------------------------------------------------
-    def _run(self, x: Tensor, t: Tensor, out: Tensor, classes: Optional[Tensor] = None, drop: Optional[Tensor] = None):
+    def _run(self, x: Tensor, t: Tensor, out: Tensor, classes: Optional[Tensor] = None, drop: Optional[Tensor] = None,
+             in_scale: Optional[Tensor] = None):
+        """in_scale (optional, fp32 [B]): per-sample factor on x folded into the WAVenc re-layout (the EDM input scale c_in of
+        the device-resident trajectory); only honoured on the tensor-core WAVenc path (`_wavenc_tc_ok`)."""
         cfg, P = self.cfg, self._pack()
         lib, dev = N.lib(), x.device
         st = N.stream_ptr(dev)
@@ -499,12 +502,14 @@ class UNet1dBase(nn.Module):
         if "to_in.tc" in P and L % W == 0:
             ent, rows = P["to_in.tc"], L // W
             xb = torch.empty(B, rows + 1, W * cin, dtype=adt, device=dev)
-            N.check(lib.adb_cl_wavenc_prep(N.ptr(x), N.ptr(xb), B, cin, L, W, S, st))
+            N.check(lib.adb_cl_wavenc_prep(N.ptr(x), N.ptr(xb), B, cin, L, W, S, N.ptr(in_scale), st))
             h = torch.empty(B, rows, 2 * nf, dtype=adt, device=dev)
             N.check(lib.adb_cl_conv(N.ptr(xb), N.ptr(ent["w"]), N.ptr(None), N.ptr(None), N.ptr(h), B, rows + 1, rows, W * cin, 2 * nf,
                                     2, 0, 1, ACT_NONE, 0, 0, 0, dt, st))
             h = h.view(B, Lc, nf)                                # row m holds frames 2m and 2m+1
         else:
+            if in_scale is not None:
+                raise N.AdbError("internal: in_scale needs the tensor-core WAVenc path")
             h = torch.empty(B, Lc, nf, dtype=adt, device=dev)
             N.check(lib.adb_cl_wavenc(N.ptr(x), N.ptr(P["to_in.to_in.weight"]), N.ptr(h), B, cin, L, nf, W, S, dt, st))
 
@@ -620,17 +625,27 @@ class UNet1dBase(nn.Module):
             return g
         cin = self.cfg["in_channels"]
         lib = N.lib()
-        buf = {k: torch.empty(B, cin, L, dtype=torch.float32, device=dev) for k in ("x", "x1", "d", "F", "net_in")}
+        P = self._pack()
+        fold_scale = "to_in.tc" in P and L % self.cfg["window_length"] == 0      # c_in folded into the WAVenc re-layout
+        buf = {k: torch.empty(B, cin, L, dtype=torch.float32, device=dev) for k in ("x", "x1", "d", "F") + (() if fold_scale else ("net_in",))}
         buf["c_noise"] = torch.empty(B, dtype=torch.float32, device=dev)
         buf["sigma"] = torch.ones(1, dtype=torch.float32, device=dev)
         buf["one"] = torch.ones(1, dtype=torch.float32, device=dev)
         buf["x"].zero_()
         buf["x1"].zero_()
 
+        buf["c_in"] = torch.empty(B, dtype=torch.float32, device=dev)
+
         def evaluate(src):
-            N.check(lib.adb_edm_precond_in(N.ptr(src), N.ptr(buf["sigma"]), 0, float(sigma_data), N.ptr(buf["net_in"]),
-                                           N.ptr(buf["c_noise"]), B, cin * L, N.stream_ptr(dev)))
-            self._run(buf["net_in"], buf["c_noise"], buf["F"])
+            if fold_scale:
+                # sigma is one value for the whole batch: broadcast it through a stride-0 read into per-sample c_in / c_noise
+                N.check(lib.adb_edm_precond_coef(N.ptr(buf["sigma"]), 0, float(sigma_data), N.ptr(buf["c_in"]), N.ptr(buf["c_noise"]), B,
+                                                 N.stream_ptr(dev)))
+                self._run(src, buf["c_noise"], buf["F"], in_scale=buf["c_in"])
+            else:
+                N.check(lib.adb_edm_precond_in(N.ptr(src), N.ptr(buf["sigma"]), 0, float(sigma_data), N.ptr(buf["net_in"]),
+                                               N.ptr(buf["c_noise"]), B, cin * L, N.stream_ptr(dev)))
+                self._run(buf["net_in"], buf["c_noise"], buf["F"])
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

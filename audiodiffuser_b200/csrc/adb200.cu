@@ -149,6 +149,19 @@ extern "C" int adb_edm_precond_in(const float* x, const float* sigmas, int sigma
     return ADB_OK;
 }
 
+// c_in(sigma_b) and c_noise(sigma_b) alone (diffusion.py:235, :240): for callers that fold the input scale into their own first
+// kernel (the U-Net's WAVenc re-layout, adb_cl_wavenc_prep) instead of running adb_edm_precond_in over the state
+__global__ void precond_prepare_kernel(const float* __restrict__ sigmas, int stride, float sigma_data, float sd2,
+                                       float* __restrict__ c_noise, float* __restrict__ c_in, int B);
+extern "C" int adb_edm_precond_coef(const float* sigmas, int sigma_stride, float sigma_data, float* c_in, float* c_noise, int B,
+                                    void* stream) {
+    REQUIRE(sigmas && c_in && c_noise && B > 0, "adb_edm_precond_coef: bad arguments");
+    REQUIRE(sigma_stride == 0 || sigma_stride == 1, "sigma_stride must be 0 or 1");
+    KL(1); precond_prepare_kernel<<<(B + 255) / 256, 256, 0, S(stream)>>>(sigmas, sigma_stride, sigma_data, sd2_of(sigma_data), c_noise, c_in, B);
+    CK(cudaGetLastError());
+    return ADB_OK;
+}
+
 extern "C" int adb_edm_precond_out(const float* x, const float* f, const float* f_null, float cond_scale,
                                    const float* sigmas, int sigma_stride, float sigma_data, float* out, int B,
                                    int64_t n_per, void* stream) {

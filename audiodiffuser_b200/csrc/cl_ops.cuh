@@ -949,20 +949,42 @@ __global__ void __launch_bounds__(256) cl_linear_batched_kernel(const float* __r
 // W = 2S an even output frame 2m reads exactly row m and an odd frame the second half of row m plus the first half of
 // row m+1 — a 2-tap GEMM-convolution over these rows (weights laid out by the host, audiodiffuser_b200/backbones/unet1d.py).
 __global__ void __launch_bounds__(256) cl_wavenc_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Cin,
-                                                             int L, long long Lp, int pad) {
+                                                             int L, long long Lp, int pad, const float* __restrict__ scale) {
+    // `scale` (per sample, or nullptr): the EDM input scale c_in(sigma) folded into the re-layout (diffusion.py:46-48 multiplies the
+    // network input by it; a separate pass over a 268 MB state otherwise)
+    if (Cin == 2 && (pad & 3) == 0 && (L & 3) == 0 && (Lp & 3) == 0) {
+        // stereo: four consecutive samples per thread: two 16-byte loads, one 16-byte store (pad, L multiples of 4: all in or all out)
+        const long long total4 = static_cast<long long>(B) * (Lp >> 2);
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const long long b = i / (Lp >> 2), j = (i - b * (Lp >> 2)) << 2;
+            const long long s0 = j - pad;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (s0 >= 0 && s0 < L) {
+                const float sc = scale ? __ldg(scale + b) : 1.0f;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(x + b * 2 * static_cast<long long>(L) + s0));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(x + (b * 2 + 1) * static_cast<long long>(L) + s0));
+                o = make_uint4(pack_bf16x2(a.x * sc, c.x * sc), pack_bf16x2(a.y * sc, c.y * sc), pack_bf16x2(a.z * sc, c.z * sc),
+                               pack_bf16x2(a.w * sc, c.w * sc));
+            }
+            *reinterpret_cast<uint4*>(out + (b * Lp + j) * 2) = o;
+        }
+        return;
+    }
     const long long total = static_cast<long long>(B) * Lp;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long b = i / Lp, j = i - b * Lp;
         const long long s = j - pad;
         const bool in = s >= 0 && s < L;
+        const float sc = scale ? __ldg(scale + b) : 1.0f;
         const float* xb = x + b * Cin * static_cast<long long>(L) + s;
         __nv_bfloat16* o = out + i * Cin;
         if (Cin == 2) {
-            const float v0 = in ? __ldg(xb) : 0.f, v1 = in ? __ldg(xb + L) : 0.f;
+            const float v0 = in ? __ldg(xb) * sc : 0.f, v1 = in ? __ldg(xb + L) * sc : 0.f;
             *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v0, v1);
         } else {
-            for (int c = 0; c < Cin; ++c) o[c] = __float2bfloat16(in ? __ldg(xb + static_cast<long long>(c) * L) : 0.f);
+            for (int c = 0; c < Cin; ++c) o[c] = __float2bfloat16(in ? __ldg(xb + static_cast<long long>(c) * L) * sc : 0.f);
         }
     }
 }

@@ -51,6 +51,10 @@ long long adb_launch_count(int reset);
  * `sigmas_dev` holds 1 value (sigma_stride = 0, the sampler's scalar sigma, utils.py:41-52) or B
  * values (sigma_stride = 1, training).
  * ---------------------------------------------------------------------------------------------- */
+/* c_in[b] = (sigma_b^2 + sigma_data^2)^-1/2 and c_noise[b] = 0.25 ln(sigma_b) alone (diffusion.py:235, :240), for callers that fold
+ * the input scale into their own first kernel (adb_cl_wavenc_prep) */
+int adb_edm_precond_coef(const float* sigmas_dev, int sigma_stride, float sigma_data, float* c_in_dev, float* c_noise_dev, int B,
+                         void* stream);
 /* net_in = c_in(sigma) * x ; c_noise[b] = 0.25 ln(sigma_b)   (diffusion.py:50, :235) */
 int adb_edm_precond_in(const float* x_dev, const float* sigmas_dev, int sigma_stride, float sigma_data,
                        float* net_in_dev, float* c_noise_dev, int B, int64_t n_per, void* stream);
@@ -299,7 +303,8 @@ int adb_cl_concat(const void* a_dev, const void* b_dev, float scale_b, void* out
  * channels-last rows [B][L/W + 1][W * Cin] shifted by pad = W/2 - S/2 samples; adb_cl_conv with taps = 2 over these rows and
  * host-arranged weights [2][W * Cin][2 F] then yields frames (2m, 2m+1) in row m of [B][L/W][2 F] == [B][L/S][F]
  * (unet1d.py:572-594). */
-int adb_cl_wavenc_prep(const float* x_dev, void* rows_bf16_dev, int B, int Cin, int L, int W, int S, void* stream);
+int adb_cl_wavenc_prep(const float* x_dev, void* rows_bf16_dev, int B, int Cin, int L, int W, int S, const float* scale_dev,
+                       void* stream);     /* scale_dev: per-sample factor on x (the EDM input scale c_in, diffusion.py:46-48) or NULL */
 /* WAVenc1d (unet1d.py:572-594): x [B][Cin][L] fp32 channels-first -> [B][L/S][F] channels-last in `dtype`;
  * WAVdec1d (unet1d.py:596-622): [B][Lc][F] -> y [B][Cout][Lc*S] fp32 channels-first. w in torch layout. */
 int adb_cl_wavenc(const float* x_dev, const float* w_dev, void* out_dev, int B, int Cin, int L, int F, int W, int S, int dtype,
