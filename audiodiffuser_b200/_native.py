@@ -71,6 +71,8 @@ _SIGS = {
                                               c_void_p, c_int64, POINTER(c_int), c_void_p]),
     "adb_cl_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "adb_cl_conv_ktrim": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_void_p]),
     "adb_cl_conv_packed_elems": (c_int64, [c_int, c_int, c_int]),
     "adb_cl_pack_conv_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "adb_cl_pack_conv_weights_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -239,7 +239,10 @@ class UNet1dBase(nn.Module):
                     kk = j * f + ph
                     if kk < k:
                         wc[j, ph * ci:(ph + 1) * ci, :] = w[:, :, kk].t()
-            return gemm_weight(wc, sd[bias_name], dict(off0=-(km // 2), dil=1, ups=0, f=f))
+            meta = dict(off0=-(km // 2), dil=1, ups=0, f=f)
+            if bf16 and ci % 64 == 0 and k == f * km + 1:
+                meta["ktrim"] = ci // 64            # the last coarse tap holds ONE fine tap: only its first ci channels are non-zero
+            return gemm_weight(wc, sd[bias_name], meta)
 
         def up(name, bias_name, f):                # ConvTranspose1d weight [Cin][Cout][2f], stride f
             w = sd[name]
@@ -371,8 +374,12 @@ class UNet1dBase(nn.Module):
             else:
                 rows, L_out, shift = Lh, 0, 0
                 o = torch.empty(Bh, Lh, ent["n"], dtype=adt, device=dev)
-            N.check(lib.adb_cl_conv(N.ptr(h), N.ptr(ent["w"]), N.ptr(ent["bias"]), N.ptr(res), N.ptr(o), Bh, Lh, rows, Ch,
-                                    ent["n"], ent["taps"], ent["off0"], ent["dil"], act, ups, shift, L_out, dt, st))
+            if "ktrim" in ent and not ups:
+                N.check(lib.adb_cl_conv_ktrim(N.ptr(h), N.ptr(ent["w"]), N.ptr(ent["bias"]), N.ptr(res), N.ptr(o), Bh, Lh, rows, Ch,
+                                              ent["n"], ent["taps"], ent["off0"], ent["dil"], act, ent["ktrim"], dt, st))
+            else:
+                N.check(lib.adb_cl_conv(N.ptr(h), N.ptr(ent["w"]), N.ptr(ent["bias"]), N.ptr(res), N.ptr(o), Bh, Lh, rows, Ch,
+                                        ent["n"], ent["taps"], ent["off0"], ent["dil"], act, ups, shift, L_out, dt, st))
             return o
 
         def gn(h, gb, ss_ptr=None, ss_ld=0):

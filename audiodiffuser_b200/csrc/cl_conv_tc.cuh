@@ -52,6 +52,8 @@ struct ClConvTcParams {
     int tiles_n;            // N / NT
     int kb_per_tap;         // Cin / 64
     int epi_warps;          // 4 (block of 192 threads) or 8 (block of 320): the fused gate epilogues need the second set
+    int nkb;                // K-blocks to run: taps * kb_per_tap, or fewer when the LAST tap's trailing blocks are all-zero weights (the
+                            // strided convolution on the [L/f][f*C] view, unet1d.py:214-225: its third coarse tap holds one fine tap)
     int kb1;                // K-blocks per tap that come from the first input; the rest from the second (channel concatenation
                             // of two tensors, unet1d.py:552-556); = kb_per_tap for a single input
 };
@@ -108,7 +110,7 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
-    const int nkb = a.taps * p.kb_per_tap;
+    const int nkb = p.nkb;
     const int pair_id = static_cast<int>(blockIdx.x) >> 1, num_pairs = static_cast<int>(gridDim.x) >> 1;
     const int total_groups = ((p.tiles_m + 1) >> 1) * p.tiles_n;     // a group = two adjacent m-tiles (one per CTA) of one n-tile
     const uint32_t stage_tx = CT_A_BYTES + static_cast<uint32_t>(p.NT) * 64u;      // this CTA's bytes per stage

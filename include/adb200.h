@@ -236,6 +236,11 @@ int adb_cl_conv(const void* in_dev, const void* w_dev, const float* bias_dev, co
                 int L_in, int rows, int Cin, int N, int taps, int off0, int dil, int act, int ups, int shift, int L_out,
                 int dtype, void* stream);
 int64_t adb_cl_conv_packed_elems(int Cin, int N, int taps);
+/* adb_cl_conv (plain store) that runs only the first `last_tap_blocks` 64-channel K-blocks of the LAST tap: for packed weights
+ * whose remaining rows of that tap are all zero — Downsample1d on the [L/f][f*C] view (unet1d.py:214-225), whose third coarse tap
+ * holds a single fine tap (k = 2f + 1), so 3 of its 4 (f = 4) phase blocks would multiply zeros. fp32 ignores the hint. */
+int adb_cl_conv_ktrim(const void* in_dev, const void* w_dev, const float* bias_dev, const void* res_dev, void* out_dev, int B, int L_in,
+                      int rows, int Cin, int N, int taps, int off0, int dil, int act, int last_tap_blocks, int dtype, void* stream);
 int adb_cl_pack_conv_weights(const float* w_f32_dev, void* packed_bf16_dev, int Cin, int N, int taps, void* stream);
 /* the same blocks in fp16: the weight operand of adb_cl_gn_conv3, whose activation operand is produced in fp16 by the fused
  * GroupNorm / SiLU transform (11 significand bits instead of bf16's 8, and a SiLU that costs one packed MUFU per two elements) */
