@@ -109,6 +109,10 @@ cl_conv3_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_in1, const __grid_c
     __syncthreads();
     cluster_sync_all();
     tc_fence_after_sync();
+    // everything above touched only this CTA's shared memory / TMEM: under programmatic dependent launch it overlaps the tail of
+    // the previous kernel; global memory is first read (and written) below
+    pdl_wait();
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
     const int pair_id = static_cast<int>(blockIdx.x) >> 1, num_pairs = static_cast<int>(gridDim.x) >> 1;
     const int groups_m = (p.tiles_m + 1) >> 1;       // a group = two adjacent m-tiles (one per CTA) of one n-tile

@@ -109,6 +109,8 @@ cl_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     __syncthreads();
     cluster_sync_all();
     tc_fence_after_sync();
+    pdl_wait();                    // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
     const int nkb = p.nkb;
     const int pair_id = static_cast<int>(blockIdx.x) >> 1, num_pairs = static_cast<int>(gridDim.x) >> 1;

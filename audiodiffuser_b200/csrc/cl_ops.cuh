@@ -634,6 +634,8 @@ __global__ void __launch_bounds__(256) cl_gn_stats_vec_kernel(const T* __restric
     const int rows_per = (L + chunks - 1) / chunks;
     const int r0 = chunk * rows_per, r1 = min(L, r0 + rows_per);
     __shared__ double sd[2][256];
+    pdl_wait();                    // programmatic dependent launch (a no-op otherwise): the input is the previous kernel's output
+    pdl_launch_dependents();
     const T* base = in + static_cast<long long>(b) * L * C;
     const int rstep = 256 / vpr, rofs = threadIdx.x / vpr, v = threadIdx.x % vpr;
     double ds = 0.0, dss = 0.0;

@@ -379,6 +379,11 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Programmatic dependent launch: `pdl_wait` blocks until the grids this one depends on have completed and their memory is visible
+// (a no-op for a normally launched kernel); `pdl_launch_dependents` lets the next kernel of the stream start its prologue
+// (barrier init, TMEM allocation, descriptor prefetch) on SMs this grid no longer occupies.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // orders generic-proxy and async-proxy (TMA) accesses of this thread in both directions, all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
