@@ -369,10 +369,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, f
 // WgradTcParams::colsum_mode) and also writes db1[j] = sum_b S_all[b][j].
 //   tap 0 (t - d >= 0): S_all - S_lo ;  tap 1: S_all ;  tap 2 (t + d < L): S_all - S_hi.   gw1: [3][C][N] fp32, N = 2C.
 // grid (N / 256, C / 8, 3 taps), 256 threads: a thread owns one column j and eight rows i; p of the block's rows sits in shared memory.
+// grid.z = 3 * layers runs every block's correction in ONE launch (layer = z / 3): p, S, gw1 and db1 advance by the given strides.
 __global__ void __launch_bounds__(256) wgrad_pcorr_kernel(const float* __restrict__ p /*[B][C]*/, const float* __restrict__ S /*[3][B][N]*/,
-                                                          float* __restrict__ gw1, float* __restrict__ db1, int B, int C, int N) {
+                                                          float* __restrict__ gw1, float* __restrict__ db1, int B, int C, int N,
+                                                          long long gw_stride, long long db_stride) {
     __shared__ float ps[64 * 8];                              // [b][8 rows], B <= 64 per pass
-    const int j = blockIdx.x * 256 + threadIdx.x, i0 = blockIdx.y * 8, tap = blockIdx.z;
+    const int layer = blockIdx.z / 3;
+    p += static_cast<long long>(layer) * B * C; S += static_cast<long long>(layer) * 3 * B * N;
+    gw1 += layer * gw_stride; db1 += layer * db_stride;
+    const int j = blockIdx.x * 256 + threadIdx.x, i0 = blockIdx.y * 8, tap = blockIdx.z % 3;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float tot = 0.f;
     for (int b0 = 0; b0 < B; b0 += 64) {
@@ -598,6 +603,61 @@ __global__ void __launch_bounds__(256) wn_bwd_apply_kernel(const float* __restri
     const float s = scale[0];                       // g / ||v||
     const float nrm = g[0] / s;                     // ||v||
     const float d = dot[0];
+    const float k = d / (nrm * nrm);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        const int ci = static_cast<int>((i / Cout) % Cin);
+        const int tap = static_cast<int>(i / (static_cast<long long>(Cout) * Cin));
+        const long long j = (static_cast<long long>(co) * Cin + ci) * taps + tap;
+        dv[j] = s * (dw[i] - v[j] * k);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) dg[0] = d / nrm;
+}
+
+// The same two passes for BOTH weight-normed convolutions of EVERY residual block in one launch each (grid.y = 2 * layers:
+// job y = block y / 2, conv y % 2: 0 = dilated conv (3 taps), 1 = output projection): 148 tiny launches per step otherwise.
+// Parameters and gradients of the blocks lie at constant strides in the device parameter copy / the flat gradient.
+struct WnLayersArgs {
+    const float* gw;        // [layers][(3 + 1) * C * 2C]: per block dW1 (3 taps) then dW2, packed [taps][Cin][Cout]
+    long long gw_stride;
+    const float *v1, *g1, *v2, *g2;     // block 0 in the device parameter copy (pieces padded to 64 floats); + layer * param_stride
+    float *dv1, *dg1, *dv2, *dg2;       // block 0 in the flat gradient (unpadded state_dict order); + layer * grad_stride
+    long long param_stride, grad_stride;
+    const float* scale;     // d_scale: [1 + 2 l] dilated conv, [2 + 2 l] output projection
+    float* dots;            // [2 * layers], zero before the dot pass
+    int C;
+};
+__global__ void __launch_bounds__(256) wn_bwd_dot_layers_kernel(WnLayersArgs a) {
+    const int layer = blockIdx.y >> 1, which = blockIdx.y & 1;
+    const int Cout = 2 * a.C, Cin = a.C, taps = which ? 1 : 3;
+    const float* dw = a.gw + layer * a.gw_stride + (which ? 3LL * Cin * Cout : 0);
+    const float* v = (which ? a.v2 : a.v1) + layer * a.param_stride;
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    float acc = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        const int ci = static_cast<int>((i / Cout) % Cin);
+        const int tap = static_cast<int>(i / (static_cast<long long>(Cout) * Cin));
+        acc = fmaf(dw[i], v[(static_cast<long long>(co) * Cin + ci) * taps + tap], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(a.dots + blockIdx.y, acc);
+}
+__global__ void __launch_bounds__(256) wn_bwd_apply_layers_kernel(WnLayersArgs a) {
+    const int layer = blockIdx.y >> 1, which = blockIdx.y & 1;
+    const int Cout = 2 * a.C, Cin = a.C, taps = which ? 1 : 3;
+    const float* dw = a.gw + layer * a.gw_stride + (which ? 3LL * Cin * Cout : 0);
+    const float* v = (which ? a.v2 : a.v1) + layer * a.param_stride;
+    const float* g = (which ? a.g2 : a.g1) + layer * a.param_stride;
+    float* dv = (which ? a.dv2 : a.dv1) + layer * a.grad_stride;
+    float* dg = (which ? a.dg2 : a.dg1) + layer * a.grad_stride;
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    const float s = a.scale[1 + which + 2 * layer];       // g / ||v||
+    const float nrm = g[0] / s;                            // ||v||
+    const float d = a.dots[blockIdx.y];
     const float k = d / (nrm * nrm);
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
