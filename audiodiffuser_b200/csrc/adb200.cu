@@ -409,6 +409,8 @@ struct adb_wavenet {
     const float** d_bp = nullptr;
     // tensor-core path (C == 256 only)
     __nv_bfloat16* wtc = nullptr;     // [layers][32][256][64]
+    __nv_bfloat16* ws16 = nullptr;    // [layers][4][256][64] bf16 skip half of W2 (training: bf16 z stash, bf16 skip GEMM)
+    CUtensorMap tm_ws16;              // its map with 128-row boxes (CTA-pair halves)
     __nv_bfloat16* wsp_tc = nullptr;  // [4][256][64]
     float* mtab = nullptr;            // [512][layers*3*512]  (W1[tap] Wp)^T
     float* cvec = nullptr;            // [layers*3*512]       W1[tap] bp (+ b1 for the centre tap)
@@ -727,6 +729,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
     }
     if (C == TC_C) {
         CKN(dmalloc(n, &n->wtc, static_cast<size_t>(layers) * 32 * 256 * 64));
+        CKN(dmalloc(n, &n->ws16, static_cast<size_t>(layers) * 4 * 256 * 64));
         CKN(dmalloc(n, &n->wsp_tc, 4ULL * 256 * 64));
         const long long ldm = static_cast<long long>(layers) * 1536;
         CKN(dmalloc(n, &n->wsp_p, static_cast<size_t>(C) * C));
@@ -752,6 +755,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
         int rc2 = make_weight_map(&n->tm_w, n->wtc, static_cast<uint64_t>(layers) * 32 * 256);
         if (!rc2) rc2 = make_weight_map(&n->tm_w2, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 128);
         if (!rc2) rc2 = make_weight_map(&n->tm_w4, n->wtc, static_cast<uint64_t>(layers) * 32 * 256, 64);
+        if (!rc2) rc2 = make_weight_map(&n->tm_ws16, n->ws16, static_cast<uint64_t>(layers) * 4 * 256, 128);
         if (!rc2) rc2 = make_weight_map(&n->tm_wsp, n->wsp_tc, 4 * 256);
         if (!rc2) rc2 = make_weight_map(&n->tm_wsp2, n->wsp_tc, 4 * 256, 128);
         {
@@ -806,6 +810,7 @@ extern "C" int adb_wavenet_create(adb_wavenet** out, int C, int layers, int cycl
             r.wpT = n->wpT + static_cast<size_t>(l) * 512 * C;
             r.b1p = w.b1p;
             r.wtc = n->wtc ? n->wtc + static_cast<size_t>(l) * 32 * 256 * 64 : nullptr;
+            r.ws16 = n->ws16 ? n->ws16 + static_cast<size_t>(l) * 4 * 256 * 64 : nullptr;
             r.w1p = w.w1p; r.w2Tp = w.w2Tp; r.w1dp = w.w1dp;
         }
         CKN(dmalloc(n, &n->d_refold, layers));
@@ -1052,6 +1057,9 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 memset(&bp, 0, sizeof bp);
                 bp.E = w.E; bp.b2 = n->L[l].b2; bp.h_in = hin; bp.h_out_dbg = hout;
                 bp.y_out = y_save ? y_save + static_cast<long long>(l) * BL * 2 * C : nullptr;
+                // training: the stash slot of this block receives z as bf16 (what the backward's weight-gradient GEMM takes; the fp16
+                // stash of the sampling path would need a re-typing pass per block) and the skip GEMM below runs in bf16
+                bp.zb_out = y_save ? w.stash + static_cast<long long>(slot) * BL * C : nullptr;
                 bp.B = bc; bp.L = L; bp.layer = l; bp.layers = layers; bp.dil = 1 << (l % n->cycle);
                 bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
                 bp.write_h = (l + 1 < layers) ? 1 : 0;
@@ -1083,8 +1091,9 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 sp.accumulate = sp.layer0 > 0 ? 1 : 0;
                 sp.bias = sp.accumulate ? nullptr : n->skip_bias;
                 sp.B = bc; sp.L = L; sp.tiles_per_b = tiles_per_b; sp.num_tiles = num_tiles;
+                sp.w_bf16 = y_save ? 1 : 0;
                 lc.dynamicSmemBytes = SKIP_GEMM_SMEM_BYTES;
-                CK(cudaLaunchKernelEx(&lc, wavenet_skip_gemm_kernel, m_zld, n->tm_w2, m_skip, sp));
+                CK(cudaLaunchKernelEx(&lc, wavenet_skip_gemm_kernel, m_zld, y_save ? n->tm_ws16 : n->tm_w2, m_skip, sp));
             }
         }
         if (!fused_tail) {

@@ -356,6 +356,12 @@ __device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
     asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
+// packed fp16 pair -> packed bf16 pair (round to nearest even)
+__device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t v) {
+    float lo, hi;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(v));
+    return pack_bf16x2(lo, hi);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

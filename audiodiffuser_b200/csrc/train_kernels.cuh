@@ -154,6 +154,7 @@ struct RefoldLayer {
     const float *v1, *v2, *wp, *b1, *s1, *s2;
     float *w1f, *w2f, *w2T, *w1d, *wpT, *b1p;
     __nv_bfloat16 *wtc, *w1p, *w2Tp, *w1dp;
+    __nv_bfloat16* ws16;    // [4][256][64] bf16 copy of the skip half of W2 (blocks 28..31 of wtc hold it in fp16): training's bf16 skip GEMM
 };
 
 __device__ __forceinline__ int gate_perm_src(int np, int C) {      // column np of the permuted layout <- original column
@@ -206,8 +207,10 @@ __global__ void __launch_bounds__(256) refold_layers_kernel(const RefoldLayer* _
                     L.wtc[i] = __float2bfloat16_rn(L.v1[(static_cast<long long>(co) * C + cib * 64 + kk) * 3 + tap] * s1);
                 } else {
                     const int j = (blk - 24) >> 2, kb = (blk - 24) & 3;
-                    const __half hv = __float2half_rn(L.v2[static_cast<long long>(256 * j + n) * C + kb * 64 + kk] * s2);
+                    const float wv = L.v2[static_cast<long long>(256 * j + n) * C + kb * 64 + kk] * s2;
+                    const __half hv = __float2half_rn(wv);
                     L.wtc[i] = *reinterpret_cast<const __nv_bfloat16*>(&hv);      // GEMM2 runs in fp16: store the fp16 bit pattern
+                    if (j == 1 && L.ws16) L.ws16[i - 28LL * 256 * 64] = __float2bfloat16_rn(wv);
                 }
                 break;
             }
@@ -234,25 +237,6 @@ __global__ void __launch_bounds__(256) refold_layers_kernel(const RefoldLayer* _
 }
 
 // dst (bf16) = src (fp32)
-// fp16 -> bf16, 8 values per thread (the z stash of the forward is fp16; the weight-gradient GEMM takes bf16 operands)
-__global__ void __launch_bounds__(256) cvt_f16_bf16_kernel(const __nv_bfloat16* __restrict__ in_f16_bits, __nv_bfloat16* __restrict__ out,
-                                                           long long n) {
-    const long long n8 = n / 8;                                 // n % 8 == 0 and 16-byte aligned buffers at every call site
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const uint4 v = reinterpret_cast<const uint4*>(in_f16_bits)[i];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
-            const float2 f = __half22float2(h);
-            const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
-            o[k] = *reinterpret_cast<const uint32_t*>(&b);
-        }
-        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-}
 
 __global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n,
                                                            float scale = 1.0f) {

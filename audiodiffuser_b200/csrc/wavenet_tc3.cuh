@@ -55,6 +55,8 @@ struct BlockZsParams {
     int B, L, layer, layers, dil;
     int tiles_per_b, num_tiles;
     int write_h;                    // 0 on the last layer (its residual output is never used, wavenet.py:145-151)
+    __nv_bfloat16* zb_out;          // training forward: this block's stash slot [B][L][256], written as bf16 from registers instead of
+                                    // the fp16 TMA store (the backward's weight-gradient GEMM and the training skip GEMM take bf16)
     int zrow0;                      // first "batch" coordinate of this layer's slot in the stash map (slot * B)
     int hi_roles;                   // 1: producer / MMA issuer on warps 8 / 9 (highest scheduler priority), epilogue on 0..7
     // multi-layer launch (ML = true): all blocks of the chunk in wavefront order
@@ -351,9 +353,24 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
                 }
             fence_proxy_async_smem();
             __syncwarp();
+            if (p.zb_out) {
+                // 32 columns (2 j + half) * 64 + 32 cc .. + 31 of this thread's row: 64 contiguous bytes per cc
+                const int zt = zt0 + q * 32 + lane;
+                if (zvalid && zt < p.L) {
+                    __nv_bfloat16* zr = p.zb_out + (static_cast<long long>(zb) * p.L + zt) * TC_C + (2 * j + half) * 64;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t lo[8], hi[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { lo[i] = f16x2_to_bf16x2(zp[cc][i]); hi[i] = f16x2_to_bf16x2(zp[cc][8 + i]); }
+                        stg256(zr + cc * 32, lo);
+                        stg256(zr + cc * 32 + 16, hi);
+                    }
+                }
+            }
             if (lane == 0) {
                 mbar_arrive_cluster(&bar_zready[j], 0);
-                if (zvalid && !(kdbg & 8)) {
+                if (zvalid && !p.zb_out && !(kdbg & 8)) {
                     // 1024 (timing experiment): every CTA stores to its own fixed tile, so the stores never leave L2
                     const int st0 = (kdbg & 1024) ? (static_cast<int>(blockIdx.x) % p.tiles_per_b) * TC_TILE_T : zt0;
                     const int sb = (kdbg & 1024) ? static_cast<int>(blockIdx.x) / p.tiles_per_b : zb;
@@ -594,6 +611,8 @@ struct SkipGemmParams {
     int G;                          // layers in this group (stash slots 0 .. G-1)
     int layer0;                     // first layer of the group (weight blocks)
     int accumulate;                 // 0: skip = value   1: skip += value (TMA reduce-add)
+    int w_bf16;                     // 1 (training): the stash and the weights are bf16; tm_w is the [layers][4][256][64] bf16 copy of the
+                                    // skip half of W2 instead of the fp16 blocks 28..31 of every layer
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -638,7 +657,7 @@ wavenet_skip_gemm_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_
     cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
-    constexpr uint32_t IDESC_F16 = umma_idesc_pair_f16(256);
+    const uint32_t IDESC_F16 = p.w_bf16 ? umma_idesc_pair_bf16(256) : umma_idesc_pair_f16(256);     // operand format of stash and weights
 
     const int pair_id = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
@@ -658,7 +677,7 @@ wavenet_skip_gemm_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_
                     uint8_t* sa = smem + SkipGemmSmem::stages + stage * T3_STAGE_BYTES;
                     uint8_t* sb = sa + T3_A_BYTES;
                     const int l = kb >> 2, cib = kb & 3;
-                    const int wblk = (p.layer0 + l) * TC_W_BLOCKS_PER_LAYER + 28 + cib;
+                    const int wblk = p.w_bf16 ? (p.layer0 + l) * 4 + cib : (p.layer0 + l) * TC_W_BLOCKS_PER_LAYER + 28 + cib;
                     if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * T3_STAGE_BYTES);
                     else        mbar_arrive_cluster(&bar_full[stage], 0);
                     tma_load_3d_pair(sa, &tm_z, &bar_full[stage], cib * 64, t0, l * p.B + b);
