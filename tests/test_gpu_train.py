@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_l2
+from conftest import record_parity, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -77,6 +77,7 @@ def test_bf16_tensor_core_training_step(dev, name):
     dev_ = sorted(((abs(a - b) / (abs(b) + 1e-3 * total), k) for k, a, b in zip(net.state_dict().keys(), norms, g["grad64_norms"])),
                   reverse=True)
     print(f"{name} bf16: grad rel-L2 vs fp64 {e64:.3e}, worst per-parameter norm deviations {[(round(d, 4), k) for d, k in dev_[:3]]}")
+    record_parity(f"{name}_bf16_gradient", rel_l2_vs_fp64=e64, worst_parameter_norm_deviation=dev_[0][0])
     assert e64 < 3e-2, e64
     # per-parameter norms within 10 % (+ 0.1 % of the whole gradient norm: the scalar weight-norm gains have tiny gradients
     # that are differences of large terms)
