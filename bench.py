@@ -430,8 +430,9 @@ def run_train(args, rank, world, local_rank):
                 "gpu_launches": int(launches), "effective_tflops": flop_step * args.steps / (ms_res * 1e-3) / 1e12, "clocks": clk}
         peaks = load_peaks()
         per_gpu = line["effective_tflops"] / world             # the roofline is one GPU's: whole-job rate / number of GPUs
-        line["roofline"] = {"bound": "tensor", "kernel": "whole training step (forward pair kernel + cl_conv_tc dgrad + wgrad_tc + element-wise; "
-                                                          "3 x 606 GFLOP per sample)",
+        line["roofline"] = {"bound": "tensor", "kernel": "whole training step (z-stash forward with a bf16 stash + bf16 skip GEMM, CTA-pair cl_conv_tc dgrad, "
+                                                          "wgrad_tc_pair, batched weight-norm / step-embedding tails, AdamW + refold; 3 x 606 GFLOP per sample; "
+                                                          "launch list profiles/r2_launches_train_bf16_b32.csv)",
                             "achieved": per_gpu, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s (per GPU)",
                             "frac": per_gpu / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"]}
         if not args.no_cpu_baseline and world == 1:       # host baseline: rank 0 at N = 1 only
