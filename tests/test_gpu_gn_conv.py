@@ -125,3 +125,60 @@ def test_conv_cat_vs_conv_on_concatenation(dev, B, L, C1, C2, N, taps):
                                  off0, 1, 0, st))
     Nn.check_async()
     assert torch.equal(out, ref)                          # same K order, same operands: bit-identical
+
+
+def test_conv_ktrim_skips_only_zero_blocks(dev):
+    """adb_cl_conv_ktrim on a strided-convolution weight (Downsample1d on the [L/f][f*C] view, unet1d.py:214-225: kernel 2f + 1, the
+    third coarse tap holds ONE fine tap) must be bit-identical to adb_cl_conv on the same packed weights: the skipped K-blocks
+    multiply zeros."""
+    from audiodiffuser_b200 import _native as Nn
+    lib, st = Nn.lib(), Nn.stream_ptr(dev)
+    B, L, ci, f, co = 3, 1000, 128, 4, 256
+    gen = torch.Generator().manual_seed(7)
+    w = torch.randn(co, ci, 2 * f + 1, generator=gen) / math.sqrt(ci * (2 * f + 1))
+    wc = torch.zeros(3, f * ci, co)
+    for j in range(3):
+        for ph in range(f):
+            kk = j * f + ph
+            if kk < 2 * f + 1:
+                wc[j, ph * ci:(ph + 1) * ci, :] = w[:, :, kk].t()
+    wc = wc.to(dev)
+    bias = (0.1 * torch.randn(co, generator=gen)).to(dev)
+    x = torch.randn(B, L // f, f * ci, generator=gen).to(dev).to(torch.bfloat16)          # the [L/f][f*C] view
+    packed = torch.empty(lib.adb_cl_conv_packed_elems(f * ci, co, 3), dtype=torch.bfloat16, device=dev)
+    Nn.check(lib.adb_cl_pack_conv_weights(Nn.ptr(wc), Nn.ptr(packed), f * ci, co, 3, st))
+    rows = L // f
+    full = torch.empty(B, rows, co, dtype=torch.bfloat16, device=dev)
+    trim = torch.empty_like(full)
+    Nn.check(lib.adb_cl_conv(Nn.ptr(x), Nn.ptr(packed), Nn.ptr(bias), Nn.ptr(None), Nn.ptr(full), B, rows, rows, f * ci, co, 3, -1, 1, 0, 0, 0, 0, 1, st))
+    Nn.check(lib.adb_cl_conv_ktrim(Nn.ptr(x), Nn.ptr(packed), Nn.ptr(bias), Nn.ptr(None), Nn.ptr(trim), B, rows, rows, f * ci, co, 3, -1, 1, 0,
+                                   ci // 64, 1, st))
+    Nn.check_async()
+    assert torch.equal(trim, full)
+    want = F.conv1d(x.double().reshape(B, L, ci).transpose(1, 2), w.to(dev).to(torch.bfloat16).double(), bias.double(), stride=f, padding=f)
+    assert rel_l2(trim, want.transpose(1, 2)) < 4e-3
+
+
+def test_wavenc_prep_folds_the_input_scale(dev):
+    """adb_cl_wavenc_prep with a per-sample scale == the same re-layout of the pre-scaled input (the EDM input scale c_in of the
+    device-resident U-Net trajectory, diffusion.py:46-48), and adb_edm_precond_coef yields the c_in / c_noise that
+    adb_edm_precond_in applies."""
+    from audiodiffuser_b200 import _native as Nn
+    lib, st = Nn.lib(), Nn.stream_ptr(dev)
+    B, cin, L, W, S = 3, 2, 4096, 32, 16
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(B, cin, L, generator=gen).to(dev)
+    sig = torch.tensor([0.7], device=dev)
+    c_in, c_noise = torch.empty(B, device=dev), torch.empty(B, device=dev)
+    Nn.check(lib.adb_edm_precond_coef(Nn.ptr(sig), 0, 0.2, Nn.ptr(c_in), Nn.ptr(c_noise), B, st))
+    net_in, c_noise2 = torch.empty_like(x), torch.empty(B, device=dev)
+    Nn.check(lib.adb_edm_precond_in(Nn.ptr(x), Nn.ptr(sig), 0, 0.2, Nn.ptr(net_in), Nn.ptr(c_noise2), B, cin * L, st))
+    rows = L // W + 1
+    a = torch.empty(B, rows, W * cin, dtype=torch.bfloat16, device=dev)
+    b = torch.empty_like(a)
+    Nn.check(lib.adb_cl_wavenc_prep(Nn.ptr(x), Nn.ptr(a), B, cin, L, W, S, Nn.ptr(c_in), st))
+    Nn.check(lib.adb_cl_wavenc_prep(Nn.ptr(net_in), Nn.ptr(b), B, cin, L, W, S, Nn.ptr(None), st))
+    Nn.check_async()
+    assert torch.equal(c_noise, c_noise2)
+    assert torch.allclose(c_in, torch.full((B,), (0.7 ** 2 + 0.2 ** 2) ** -0.5, device=dev), rtol=1e-6)
+    assert torch.equal(a, b)
