@@ -1041,7 +1041,9 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
             // sits in front of the current item's last job. That is only safe while the next item (pairs items later) cannot depend,
             // directly or transitively, on the current one, i.e. while a layer of a sub-pass has more groups than pairs + the widest
             // neighbourhood (17 tiles); otherwise the plain order, whose waits only ever precede an item's own jobs.
-            const bool use_pipe = n->zs_pipe && (bp.ml_S * tiles_per_b + 1) / 2 > pairs + 17;
+            // (the ragged last sub-pass counts: it is the one with the fewest groups per layer)
+            const int groups_min = rem ? (rem * tiles_per_b + 1) / 2 : (bp.ml_S * tiles_per_b + 1) / 2;
+            const bool use_pipe = n->zs_pipe && groups_min > pairs + 17;
             if (use_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
             else          CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<false, true>, m_hA, n->tm_w2, m_hBo, m_zst, m_hB, m_hAo, bp));
         }

@@ -272,7 +272,7 @@ def test_zstash_passes_and_layer_groups(dev, monkeypatch, chunk, stash_gb):
         assert torch.equal(out, base)                                  # passes alone do not change a single bit
 
 
-@pytest.mark.parametrize("S,pipe", [(1, 0), (2, 0), (2, 1), (5, 1)])
+@pytest.mark.parametrize("S,pipe", [(1, 0), (2, 0), (2, 1), (5, 1), (4, 1)])
 def test_multilayer_wavefront_launch_is_bit_identical(dev, monkeypatch, S, pipe):
     """ADB_ZS_ML = S (opt-in): all blocks of a chunk in ONE launch as a wavefront over (sub-pass of S samples, layer,
     tile group) with per-tile completion flags, ping / pong reused in L2. Same arithmetic per tile, so the waveforms must be
