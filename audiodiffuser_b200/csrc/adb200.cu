@@ -973,8 +973,11 @@ static int sm_count() {
 // `emb` ([B][512], embed_mlp_kernel) is already in w.emb.
 // Training forward (h_save / y_save non-null, one pass over the whole batch): block l reads h_save slot l and writes slot l + 1, and
 // leaves its pre-gate activations in y_save slot l; the stash then holds every block's z (w.G == layers).
+// `uniform`: every sample has the same noise level (the sampler's scalar sigma): the step embedding and the E constants are computed
+// for ONE sample (w.emb row 0) and shared (the per-sample E GEMM was 0.8 % of an evaluation).
 static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale, int in_scale_stride, float* out, int B, int L,
-                           const Workspace& w, cudaStream_t st, __nv_bfloat16* h_save = nullptr, __nv_bfloat16* y_save = nullptr) {
+                           const Workspace& w, cudaStream_t st, __nv_bfloat16* h_save = nullptr, __nv_bfloat16* y_save = nullptr,
+                           bool uniform = false) {
     REQUIRE(!h_save || (w.Bc == B && w.G == n->layers), "internal: the training forward needs a whole-batch workspace with a full stash");
     const int C = n->C, layers = n->layers;
     const int num_sms = sm_count();
@@ -988,8 +991,8 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
             ScopedTimer t(n, ADB_TIMER_AUX, st, 2);
             ConvF32Args a;
             memset(&a, 0, sizeof a);
-            a.in = w.emb + static_cast<long long>(b0) * 512; a.w = n->mtab; a.bias = n->cvec; a.out = w.E;
-            a.nb = 1; a.L = bc; a.Cin = 512; a.Cout = layers * 1536; a.taps = 1; a.dil = 1;
+            a.in = uniform ? w.emb : w.emb + static_cast<long long>(b0) * 512; a.w = n->mtab; a.bias = n->cvec; a.out = w.E;
+            a.nb = 1; a.L = uniform ? 1 : bc; a.Cin = 512; a.Cout = layers * 1536; a.taps = 1; a.dil = 1;
             a.ldw = static_cast<long long>(layers) * 1536; a.ldo = a.ldw; a.in_scale = 1.f;
             CK(conv_cl_f32(a, st));
             in_proj_kernel<true><<<grid_for(BL * (C / 8)), 256, 0, st>>>(
@@ -1030,7 +1033,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
             bp.tiles_per_b = tiles_per_b; bp.num_tiles = num_tiles;
             bp.write_h = 1;                       // uniform job structure; the last block's h' stores are skipped in the kernel
             bp.zrow0 = 0; bp.hi_roles = n->zs_hi_roles; bp.dbg = n->dbg;
-            bp.b2_tab = n->d_b2; bp.ml_flags = w.ml_flags; bp.cycle = n->cycle;
+            bp.b2_tab = n->d_b2; bp.ml_flags = w.ml_flags; bp.cycle = n->cycle; bp.e_uniform = uniform ? 1 : 0;
             bp.ml_S = n->zs_ml_S < bc ? n->zs_ml_S : bc;
             const int full_sp = bc / bp.ml_S, rem = bc % bp.ml_S;
             bp.ml_items_per_sp = layers * ((bp.ml_S * tiles_per_b + 1) / 2);
@@ -1067,6 +1070,7 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
                 bp.write_h = (l + 1 < layers) ? 1 : 0;
                 bp.zrow0 = slot * bc;
                 bp.hi_roles = n->zs_hi_roles;
+                bp.e_uniform = uniform ? 1 : 0;
                 bp.dbg = n->dbg;
                 lc.dynamicSmemBytes = TC3_SMEM_BYTES;
                 if (n->zs_pipe) CK(cudaLaunchKernelEx(&lc, wavenet_block_zs_kernel<true, false>, m_h, n->tm_w2, m_hout, m_zst, m_h, m_hout, bp));
@@ -1114,14 +1118,17 @@ static int forward_bf16_zs(adb_wavenet* n, const float* x, const float* in_scale
 
 static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, const float* in_scale, int in_scale_stride,
                         float* out, int B, int L, int precision, const Workspace& w, float* dump_h, float* dump_skip,
-                        int dump_layers, cudaStream_t st, __nv_bfloat16* h_save = nullptr, __nv_bfloat16* y_save = nullptr) {
+                        int dump_layers, cudaStream_t st, __nv_bfloat16* h_save = nullptr, __nv_bfloat16* y_save = nullptr,
+                        bool uniform_sigma = false) {
     // h_save (bf16 path, training): [layers][B][L][C]; block l reads slot l and writes slot l + 1 instead of ping-ponging.
     // y_save (z-stash path, training): [layers][B][L][2C], every block's pre-gate activations, so the backward recomputes nothing.
     const int C = n->C, layers = n->layers;
     const long long BL = static_cast<long long>(B) * L;
     {
         ScopedTimer t(n, ADB_TIMER_AUX, st);
-        embed_mlp_kernel<<<B, 512, 0, st>>>(c_noise, n->fc1w, n->fc1b, n->fc2w, n->fc2b, w.emb);
+        // one embedding for the whole batch when the z-stash path runs with a scalar sigma (see forward_bf16_zs)
+        const bool zs_uniform = uniform_sigma && precision == ADB_PRECISION_BF16 && dump_layers == 0 && n->block_kernel == 3 && !h_save;
+        embed_mlp_kernel<<<zs_uniform ? 1 : B, 512, 0, st>>>(c_noise, n->fc1w, n->fc1b, n->fc2w, n->fc2b, w.emb);
         CK(cudaGetLastError());
     }
     if (precision == ADB_PRECISION_FP32) {
@@ -1172,7 +1179,7 @@ static int forward_impl(adb_wavenet* n, const float* x, const float* c_noise, co
 
     // ---------------- bf16 tensor-core path ----------------
     if (dump_layers == 0 && n->block_kernel == 3 && (!h_save || y_save))
-        return forward_bf16_zs(n, x, in_scale, in_scale_stride, out, B, L, w, st, h_save, y_save);
+        return forward_bf16_zs(n, x, in_scale, in_scale_stride, out, B, L, w, st, h_save, y_save, uniform_sigma && !h_save);
     REQUIRE(w.Bc == B, "internal: the pair-kernel path needs a whole-batch workspace (B=%d, pass=%d)", B, w.Bc);
     {
         ScopedTimer t(n, ADB_TIMER_AUX, st, 2);
@@ -1306,7 +1313,7 @@ extern "C" int adb_wavenet_denoise(adb_wavenet* n, const float* x, const float* 
     precond_prepare_kernel<<<(B + 255) / 256, 256, 0, st>>>(sigmas, sigma_stride, sigma_data, sd2_of(sigma_data), w.c_noise,
                                                             w.c_in, B);
     CK(cudaGetLastError());
-    rc = forward_impl(n, x, w.c_noise, w.c_in, 1, w.fbuf, B, L, precision, w, nullptr, nullptr, 0, st);
+    rc = forward_impl(n, x, w.c_noise, w.c_in, 1, w.fbuf, B, L, precision, w, nullptr, nullptr, 0, st, nullptr, nullptr, sigma_stride == 0);
     if (rc) return rc;
     return adb_edm_precond_out(x, w.fbuf, nullptr, 1.0f, sigmas, sigma_stride, sigma_data, out, B, L, stream);
 }
@@ -1320,7 +1327,7 @@ static int net_eval(adb_wavenet* n, const float* x, float sigma, float sigma_dat
     fill2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.c_noise, c.c_noise, w.c_in, c.c_in, B);
     CK(cudaGetLastError());
     n->launches[ADB_TIMER_AUX]++;
-    return forward_impl(n, x, w.c_noise, w.c_in, 1, f_out, B, L, precision, w, nullptr, nullptr, 0, st);
+    return forward_impl(n, x, w.c_noise, w.c_in, 1, f_out, B, L, precision, w, nullptr, nullptr, 0, st, nullptr, nullptr, true);
 }
 
 extern "C" int adb_wavenet_sample_edm_seeded(adb_wavenet* n, const float* noise, const float* sigmas_host, int n_sigmas,

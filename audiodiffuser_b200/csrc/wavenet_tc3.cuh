@@ -59,6 +59,7 @@ struct BlockZsParams {
                                     // the fp16 TMA store (the backward's weight-gradient GEMM and the training skip GEMM take bf16)
     int zrow0;                      // first "batch" coordinate of this layer's slot in the stash map (slot * B)
     int hi_roles;                   // 1: producer / MMA issuer on warps 8 / 9 (highest scheduler priority), epilogue on 0..7
+    int e_uniform;                  // 1: every sample has the same noise level (sampling: sigma is a scalar), E holds ONE sample's constants
     // multi-layer launch (ML = true): all blocks of the chunk in wavefront order
     const __nv_bfloat16* h_in2;     // pong buffer (residual input of odd layers)
     const float* const* b2_tab;     // per-layer output-projection biases
@@ -397,7 +398,7 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             ++jg;
             if (job < 2) {
                 // ---- epilogue 1: gate ----
-                const float* Eg = p.E + (static_cast<long long>(tile_valid ? b : 0) * p.layers + layer) * 1536;
+                const float* Eg = p.E + (static_cast<long long>((tile_valid && !p.e_uniform) ? b : 0) * p.layers + layer) * 1536;
                 if (job == 0) {
                     // interior tiles (every row sees all three taps) add ONE vector: E0 + E1 + E2, gate half pre-scaled by 1/2
                     named_bar_sync(1, TC_EPI_THREADS);            // everyone is done with the previous group's vector
