@@ -28,6 +28,7 @@ _SIGS = {
     "adb_device_check": (c_int, [c_int]),
     "adb_check_async": (c_int, []),
     "adb_debug_zs_job_order": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int]),
+    "adb_debug_ml_order": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_longlong), POINTER(c_int), POINTER(c_int)]),
     "adb_launch_count": (ctypes.c_longlong, [c_int]),
     "adb_edm_precond_in": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "adb_edm_precond_out": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_float, c_void_p, c_int,

@@ -88,6 +88,44 @@ extern "C" int adb_debug_tc_cycles(unsigned long long* out16, int reset) {
     return ADB_OK;
 }
 
+// host view of the multi-layer wavefront launch (wavenet_tc3.cuh, ML = true), for the CPU test of its dependency structure: walks every
+// item of a chunk of `bc` samples in launch order and checks that each tile it must wait for belongs to an EARLIER item (a pair only
+// ever waits for items dealt before its own: no wait cycle). Returns the number of violations; min_distance = the smallest index
+// distance between an item and one of its dependencies, pipelined_ok = whether the launch would use the software-pipelined job order.
+extern "C" int adb_debug_ml_order(int bc, int L, int layers, int cycle, int S, int pairs, long long* min_distance, int* n_items,
+                                  int* pipelined_ok) {
+    const int tiles_per_b = (L + TC_TILE_T - 1) / TC_TILE_T, num_tiles = bc * tiles_per_b;
+    if (S > bc) S = bc;
+    const int full_sp = bc / S, rem = bc % S;
+    const int items_per_sp = layers * ((S * tiles_per_b + 1) / 2);
+    const int items = full_sp * items_per_sp + layers * ((rem * tiles_per_b + 1) / 2);
+    const int groups_min = rem ? (rem * tiles_per_b + 1) / 2 : (S * tiles_per_b + 1) / 2;
+    long long best = 1LL << 60;
+    int bad = 0;
+    for (int n = 0; n < items; ++n) {
+        int layer, tile0, t_end;
+        ml_item_decode(n, items_per_sp, S, tiles_per_b, num_tiles, layer, tile0, t_end);
+        if (layer == 0) continue;
+        const int sp = n / items_per_sp, t_begin = sp * S * tiles_per_b, groups = (t_end - t_begin + 1) >> 1;
+        for (int rank = 0; rank < 2; ++rank) {
+            const int tile = tile0 + rank;
+            if (tile >= t_end) continue;
+            int lo, hi;
+            ml_dep_range(layer, tile, cycle, tiles_per_b, lo, hi);
+            for (int j = lo; j <= hi; ++j) {
+                if (j < t_begin || j >= t_end) { ++bad; continue; }            // a dependency outside the sub-pass would never be signalled
+                const int dep = sp * items_per_sp + (layer - 1) * groups + ((j - t_begin) >> 1);
+                if (dep >= n) ++bad;
+                else if (n - dep < best) best = n - dep;
+            }
+        }
+    }
+    if (min_distance) *min_distance = best;
+    if (n_items) *n_items = items;
+    if (pipelined_ok) *pipelined_ok = groups_min > pairs + 17 ? 1 : 0;
+    return bad;
+}
+
 // host view of the z-stash kernel's job order (wavenet_tc3.cuh: zs_job_at), for the CPU tests of the schedule: writes up to `cap`
 // (type, group) pairs and returns how many jobs the sequence has
 extern "C" int adb_debug_zs_job_order(int n_groups, int write_h, int pipelined, int* types, int* groups, int cap) {

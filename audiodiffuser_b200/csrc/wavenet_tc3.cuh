@@ -95,6 +95,30 @@ __host__ __device__ __forceinline__ bool zs_job_at(int s, int n, int write_h, in
     return i < n;
 }
 
+// Wavefront order of the multi-layer launch, shared by the kernel and the host-side check of its dependency structure
+// (adb_debug_ml_order): item n -> its block (layer), the first tile of its group (the pair's rank-0 tile; rank 1 takes the next one)
+// and the end of its sub-pass's tile range. Sub-passes of S samples, then layers, then tile groups.
+__host__ __device__ __forceinline__ void ml_item_decode(int n, int items_per_sp, int S, int tiles_per_b, int num_tiles, int& layer,
+                                                        int& tile0, int& t_end) {
+    const int sp = n / items_per_sp, r = n - sp * items_per_sp;
+    const int t_begin = sp * S * tiles_per_b;
+    t_end = t_begin + S * tiles_per_b;
+    if (t_end > num_tiles) t_end = num_tiles;
+    const int groups = (t_end - t_begin + 1) >> 1;
+    layer = r / groups;
+    tile0 = t_begin + 2 * (r - layer * groups);
+}
+// Tiles of block layer - 1 that block `layer` of `tile` must see finished: everything it reads (+-dil rows) and everything whose
+// readers its h' store would overrun (+-previous dilation: ping / pong are reused every second block), inside the tile's sample.
+__host__ __device__ __forceinline__ void ml_dep_range(int layer, int tile, int cycle, int tiles_per_b, int& lo, int& hi) {
+    const int dil = 1 << (layer % cycle), dprev = 1 << ((layer - 1) % cycle);
+    const int dmax = dil > dprev ? dil : dprev;
+    const int kt = (dmax + TC_TILE_T - 1) / TC_TILE_T;
+    const int tb0 = (tile / tiles_per_b) * tiles_per_b, tb1 = tb0 + tiles_per_b - 1;
+    lo = tile - kt < tb0 ? tb0 : tile - kt;
+    hi = tile + kt > tb1 ? tb1 : tile + kt;
+}
+
 // ML = true: ONE launch runs ALL blocks of a 256-sample chunk as a wavefront over (sub-pass of S samples, layer, tile group): block
 // l + 1 of a tile starts as soon as block l has written the +-d neighbourhood it reads (per-tile completion flags in global
 // memory; the groups are dealt to the CTA pairs round-robin in wavefront order, so a pair only ever waits for EARLIER items and
@@ -166,13 +190,9 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             tile = (pair_id + gi * num_pairs) * 2 + rank;
             valid = tile < p.num_tiles;
         } else {
-            const int n = pair_id + gi * num_pairs;
-            const int sp = n / p.ml_items_per_sp, r = n - sp * p.ml_items_per_sp;
-            const int t_begin = sp * p.ml_S * p.tiles_per_b;
-            const int t_end = min(p.num_tiles, t_begin + p.ml_S * p.tiles_per_b);
-            const int groups = (t_end - t_begin + 1) >> 1;
-            layer = r / groups;
-            tile = t_begin + 2 * (r - layer * groups) + rank;
+            int tile0, t_end;
+            ml_item_decode(pair_id + gi * num_pairs, p.ml_items_per_sp, p.ml_S, p.tiles_per_b, p.num_tiles, layer, tile0, t_end);
+            tile = tile0 + rank;
             valid = tile < t_end;
         }
     };
@@ -195,11 +215,8 @@ wavenet_block_zs_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_c
             if (ML && job == 0 && layer > 0 && tvalid) {
                 // wavefront dependency: the previous block must have finished every tile this one reads (+-dil rows) and every tile whose
                 // readers this one's h' store would overrun (+-previous dilation: ping / pong are reused every second block)
-                const int dprev = 1 << ((layer - 1) % p.cycle);
-                const int dmax = dil > dprev ? dil : dprev;
-                const int kt = (dmax + TC_TILE_T - 1) / TC_TILE_T;
-                const int tb0 = b * p.tiles_per_b, tb1 = tb0 + p.tiles_per_b - 1;
-                const int lo = max(tile - kt, tb0), hi = min(tile + kt, tb1);
+                int lo, hi;
+                ml_dep_range(layer, tile, p.cycle, p.tiles_per_b, lo, hi);
                 const unsigned int* fl = p.ml_flags + static_cast<long long>(layer - 1) * p.num_tiles;
                 TC_DBG_T0(tf);
                 for (int j = lo + lane; j <= hi; j += 32) {

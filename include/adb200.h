@@ -38,6 +38,12 @@ int adb_device_check(int device);
 /* Host view of the z-stash residual-block kernel's job order (types 0 = G1a, 1 = G1b, 2 = G2r; wavenet_tc3.cuh): fills up to `cap`
  * (type, group) pairs and returns the number of jobs. No GPU involved; used by the CPU tests of the software-pipelined schedule. */
 int adb_debug_zs_job_order(int n_groups, int write_h, int pipelined, int* types, int* groups, int cap);
+/* Host view of the opt-in multi-layer wavefront launch (ADB_ZS_ML = S): walks every (sub-pass, layer, tile group) item of a chunk of
+ * `bc` samples in launch order and returns how many awaited tiles do NOT belong to an earlier item of the same sub-pass (0 = the
+ * round-robin dealing cannot deadlock); *min_distance = smallest index distance item -> dependency, *pipelined_ok = whether the
+ * launch would use the software-pipelined job order. Test infrastructure (tests/test_host_logic.py), no GPU needed. */
+int adb_debug_ml_order(int bc, int L, int layers, int cycle, int S, int pairs, long long* min_distance, int* n_items,
+                       int* pipelined_ok);
 
 /* Synchronise the device and report any asynchronous kernel / pipeline error (test & bench use). */
 int adb_check_async(void);

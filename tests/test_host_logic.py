@@ -225,3 +225,33 @@ def test_zstash_kernel_job_order():
                 # accumulator k & 1: the job two positions earlier used the same one; its epilogue needs that job complete,
                 # which the in-order tensor pipe guarantees — here just check the alternation covers every job once
                 assert sorted(seq) == sorted((t, i) for i in range(n) for t in range(3 if write_h else 2))
+
+
+def test_multilayer_wavefront_order_has_no_wait_cycle():
+    """The wavefront order of the opt-in multi-layer launch (ADB_ZS_ML, wavenet_tc3.cuh ML = true; the kernel and this host view
+    share ml_item_decode / ml_dep_range): items are dealt round-robin to the CTA pairs, so the launch cannot deadlock if every tile
+    an item waits for belongs to an EARLIER item and lies inside its own sub-pass (only those are ever signalled). Also checks the
+    rule that picks the plain job order whenever a layer of the smallest sub-pass is not longer than pairs + the widest
+    neighbourhood, and that the distance to the nearest dependency is what DESIGN 4.1 says (125 - 8 groups at S = 2)."""
+    import ctypes
+    from audiodiffuser_b200 import _native as N
+    lib = N.lib()
+    dist, items, pipe = ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+    cases = [(256, 16000, 36, 12, 2, 74), (256, 16000, 36, 12, 4, 74), (256, 16000, 36, 12, 5, 74), (5, 4096, 13, 12, 2, 74),
+             (5, 4096, 13, 12, 1, 74), (7, 1000, 4, 2, 3, 10), (1, 16000, 36, 12, 8, 74), (3, 130, 36, 12, 2, 74)]
+    for bc, L, layers, cycle, S, pairs in cases:
+        bad = lib.adb_debug_ml_order(bc, L, layers, cycle, S, pairs, ctypes.byref(dist), ctypes.byref(items), ctypes.byref(pipe))
+        assert bad == 0, (bc, L, layers, cycle, S, bad)
+        tiles = -(-L // 128)
+        s_eff = min(S, bc)
+        full, rem = divmod(bc, s_eff)
+        want_items = layers * (full * ((s_eff * tiles + 1) // 2) + ((rem * tiles + 1) // 2))
+        assert items.value == want_items
+        smallest = ((rem if rem else s_eff) * tiles + 1) // 2
+        assert pipe.value == (1 if smallest > pairs + 17 else 0)
+        if layers > 1:
+            assert dist.value >= 1
+    bad = lib.adb_debug_ml_order(256, 16000, 36, 12, 2, 74, ctypes.byref(dist), ctypes.byref(items), ctypes.byref(pipe))
+    assert bad == 0 and dist.value == 125 - 8 and pipe.value == 1          # 125 groups per layer, dilation 2048 = 16 tiles = 8 groups
+    bad = lib.adb_debug_ml_order(256, 16000, 36, 12, 5, 74, ctypes.byref(dist), ctypes.byref(items), ctypes.byref(pipe))
+    assert bad == 0 and pipe.value == 0                                    # 256 = 51 x 5 + 1: the ragged sub-pass has 63 groups per layer
